@@ -1,0 +1,76 @@
+"""Oracle tooling (test infrastructure): import the UNMODIFIED reference on CPU.
+
+Only usable where ``/root/reference`` exists (the build container); nothing
+under ``tests -m gpu``, ``smoke()`` or ``bench.py`` calls this.  Used by
+``oracle/make_golden.py`` to generate the committed fixtures.
+
+Recipe: put the checkout on ``sys.path``, stub the
+absent third-party imports, and make ``.cuda()`` the identity so the
+hard-coded device moves on the hot path (``diffwave_ddpm.py:66-67,100,157``)
+stay on the CPU.
+"""
+
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("AUDIOPURE_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "diffusion_models"))
+
+
+def load():
+    """Returns a namespace with the reference modules needed on the hot path."""
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REF_ROOT)
+    import torch
+    import torchaudio
+
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    for name in ("librosa", "torchsde"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if "statsmodels" not in sys.modules:
+        try:
+            importlib.import_module("statsmodels.stats.proportion")
+        except Exception:
+            sm = types.ModuleType("statsmodels")
+            sms = types.ModuleType("statsmodels.stats")
+            smp = types.ModuleType("statsmodels.stats.proportion")
+
+            def _unavailable(*a, **k):
+                raise RuntimeError("statsmodels is not installed; see oracle.certify.lower_conf_bound")
+
+            smp.proportion_confint = _unavailable
+            sys.modules["statsmodels"] = sm
+            sys.modules["statsmodels.stats"] = sms
+            sys.modules["statsmodels.stats.proportion"] = smp
+    import torchaudio.datasets.utils as tdu
+
+    for fn in ("download_url", "extract_archive"):
+        if not hasattr(tdu, fn):
+            setattr(tdu, fn, lambda *a, **k: None)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+
+    ns = types.SimpleNamespace()
+    ns.ddpm = importlib.import_module("diffusion_models.diffwave_ddpm")
+    ns.sde = importlib.import_module("diffusion_models.diffwave_sde")
+    ns.wavenet = importlib.import_module("diffusion_models.DiffWave_Unconditional.WaveNet")
+    ns.util = importlib.import_module("diffusion_models.DiffWave_Unconditional.util")
+    ns.acoustic_system = importlib.import_module("acoustic_system")
+    ns.certified = importlib.import_module("robustness_eval.certified_robust")
+    spec = importlib.util.spec_from_file_location(
+        "_ref_resnext", os.path.join(REF_ROOT, "audio_models/ConvNets_SpeechCommands/models/resnext.py"))
+    ns.resnext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ns.resnext)
+    ns.torchaudio = torchaudio
+    return ns

@@ -1,0 +1,199 @@
+"""The oracle against the fixtures generated from the unmodified reference
+(oracle/make_golden.py).  CPU only.  This is what pins the oracle."""
+
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import certify, mel, purify, resnext, schedule, wavenet, weights as W
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def hp():
+    return schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+
+
+@pytest.fixture(scope="module")
+def sd_full():
+    return W.make_state_dict(1234)
+
+
+@pytest.fixture(scope="module")
+def eps_fn(sd_full):
+    return lambda x, t: wavenet.eps_theta(sd_full, x, t)
+
+
+def test_schedule_bit_exact(golden, hp):
+    g = golden("schedule.npz")
+    for k in ("Beta", "Alpha", "Alpha_bar", "Sigma"):
+        assert np.array_equal(hp[k].numpy(), g[k]), k
+    emb = schedule.calc_diffusion_step_embedding(torch.from_numpy(g["steps"]), 128)
+    assert np.array_equal(emb.numpy(), g["emb"])
+    tab = schedule.sde_tables()
+    for k in ("discrete_betas", "alphas_cumprod", "sqrt_1m_alphas_cumprod"):
+        assert np.array_equal(tab[k].numpy(), g[k]), k
+    # the two alpha-bar flavours differ in the last ulp -- keep them separate
+    assert np.abs(tab["alphas_cumprod"].numpy() - hp["Alpha_bar"].numpy()).max() < 1e-6
+
+
+def test_t_star_table(hp):
+    # SURVEY 3.3 probe: sigma -> t*
+    for sigma, t in ((0.1, 14), (0.25, 34), (0.5, 66), (0.75, 94), (1.0, 117)):
+        assert schedule.compute_t_star(hp["Alpha_bar"], sigma)[1] == t
+
+
+def test_weights_fingerprint(golden, sd_full):
+    g = golden("wavenet_full.npz")
+    assert len(sd_full) == 408
+    assert sum(v.numel() for v in sd_full.values()) == 24071681
+    np.testing.assert_allclose(W.fingerprint(sd_full), g["fingerprint"], rtol=0, atol=0)
+    assert float(W.make_waveforms(1, 16000, 0).double().sum()) == float(g["x_checksum"])
+
+
+def test_wavenet_full(golden, sd_full):
+    g = golden("wavenet_full.npz")
+    x = W.make_waveforms(1, 16000, seed=0)
+    eps, inter = wavenet.eps_theta(sd_full, x, 1, return_intermediates=True)
+    assert rel_l2(eps, g["eps_t1"]) < 1e-5
+    idx = torch.from_numpy(g["slice_t"])
+    for n in (0, 11, 35):
+        assert rel_l2(inter["h"][n][:, :, idx], g["h_%d" % n]) < 1e-5, n
+        assert rel_l2(inter["skip"][n][:, :, idx], g["skip_%d" % n]) < 1e-5, n
+    assert float(eps.abs().max()) > 1e-3  # ZeroConv1d was re-randomised: parity is not vacuous
+    eps33 = wavenet.eps_theta(sd_full, x, 33)
+    assert rel_l2(eps33, g["eps_t33"]) < 1e-5
+    assert rel_l2(eps33, eps) > 1e-3  # the step embedding matters
+
+
+def test_wavenet_small_ragged(golden):
+    g = golden("wavenet_small.npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = W.make_state_dict(int(g["seed"]), cfg)
+    np.testing.assert_array_equal(W.fingerprint(sd), g["fingerprint"])
+    x = W.make_waveforms(3, 1000, seed=int(g["x_seed"]))
+    eps = wavenet.eps_theta(sd, x, int(g["t"]), cfg)
+    assert rel_l2(eps, g["eps"]) < 1e-5
+
+
+def test_aliasing_quirk(sd_full):
+    """the residual term is the *shifted* input."""
+    x = torch.randn(1, 256, 64, generator=torch.Generator().manual_seed(0))
+    emb = torch.randn(1, 512, generator=torch.Generator().manual_seed(1))
+    h, _, xs, gate = wavenet.residual_block(sd_full, 0, 1, x, emb)
+    wr = wavenet.fold_weight_norm(sd_full["residual_layer.residual_blocks.0.res_conv.weight_g"],
+                                  sd_full["residual_layer.residual_blocks.0.res_conv.weight_v"])
+    res = torch.nn.functional.conv1d(gate, wr, sd_full["residual_layer.residual_blocks.0.res_conv.bias"])
+    assert torch.allclose(h, (xs + res) * math.sqrt(0.5), atol=1e-6)
+    assert not torch.allclose(h, (x + res) * math.sqrt(0.5), atol=1e-3)
+
+
+@pytest.mark.parametrize("t_star", [2, 3])
+def test_ddpm_purify(golden, hp, eps_fn, t_star):
+    g = golden("ddpm_t%d.npz" % t_star)
+    x = W.make_waveforms(2, 16000, seed=int(g["x_seed"]))
+    z = W.make_noise((t_star, 2, 1, 16000), seed=int(g["z_seed"]))
+    y = purify.ddpm_purify(hp, eps_fn, x, t_star, z)
+    assert rel_l2(y, g["purified"]) < 1e-6
+    assert float((y - torch.from_numpy(g["purified"])).abs().max()) < 1e-5
+
+
+def test_one_shot(golden, hp, eps_fn):
+    g = golden("oneshot_t34.npz")
+    x = W.make_waveforms(1, 16000, seed=0)
+    y = purify.one_shot_denoise(hp, eps_fn, x, int(g["reverse_timestep"]))
+    assert rel_l2(y, g["x0_hat"]) < 1e-5
+
+
+def test_sde_drift_diffusion(golden, eps_fn):
+    g = golden("sde_fg.npz")
+    tab = schedule.sde_tables()
+    x = W.make_waveforms(1, 16000, seed=int(g["x_seed"])).view(1, -1)
+    for i, tc in enumerate(g["tc"]):
+        t = torch.tensor(tc, dtype=torch.float32)
+        f = purify.sde_f(tab, eps_fn, t, x)
+        gg = purify.sde_g(tab, t, x)
+        assert rel_l2(f, g["f"][i]) < 1e-5
+        np.testing.assert_allclose(gg[:, :4].numpy(), g["g"][i], rtol=1e-6, atol=0)
+    assert np.all(g["g"][-1] == 0)  # k == 0: no noise on the last step
+
+
+def test_sde_matches_affine_form(eps_fn):
+    """one EM step at index k is x(1+b/2) - b/sqrt(1-abar) eps + sigma_k z."""
+    tab = schedule.sde_tables()
+    t = 2
+    x0 = W.make_waveforms(1, 16000, seed=3)
+    e = W.make_noise((1, 1, 16000), seed=21)
+    z = W.make_noise((t, 1, 16000), seed=22)
+    y = purify.sde_purify(tab, eps_fn, x0, t, e, z)
+    b, ac = tab["discrete_betas"].double(), tab["alphas_cumprod"].double()
+    x = (x0.double() * ac[t - 1].sqrt() + e.double() * (1 - ac[t - 1]).sqrt()).float()
+    for i, k in enumerate(range(t - 1, -1, -1)):
+        eps = eps_fn(x, k).double()
+        sig = (b[k].sqrt() * ((1 - ac[k - 1]) / (1 - ac[k])).sqrt()) if k > 0 else 0.0
+        x = (x.double() * (1 + b[k] / 2) - b[k] / (1 - ac[k]).sqrt() * eps + sig * z[i].view(1, 1, -1).double()).float()
+    assert rel_l2(y, x) < 1e-5
+
+
+def test_log_mel(golden):
+    g = golden("mel.npz")
+    np.testing.assert_allclose(mel.melscale_fbanks().numpy(), g["fb"], rtol=0, atol=0)
+    x = torch.cat([W.make_waveforms(2, 16000, seed=0), torch.from_numpy(golden("ddpm_t2.npz")["purified"])], 0)
+    db = mel.log_mel(x)
+    assert db.shape == (4, 1, 32, 32)
+    assert float((db - torch.from_numpy(g["logmel"])).abs().max()) < 1e-3
+    # independent float64 framing + rfft agrees to fp32 rounding
+    assert float(np.abs(mel.log_mel_f64(x) - g["logmel"]).max()) < 2e-3
+
+
+def test_resnext_and_acoustic_system(golden, hp, eps_fn):
+    csd = resnext.make_state_dict(4321)
+    spec = torch.from_numpy(golden("mel.npz")["logmel"])
+    logits = resnext.forward(csd, spec)
+    assert rel_l2(logits, golden("resnext.npz")["logits"]) < 1e-5
+    g = golden("acoustic.npz")
+    x = W.make_waveforms(2, 16000, seed=0)
+    nodef = resnext.forward(csd, mel.log_mel(x))
+    assert rel_l2(nodef, g["logits_nodefend"]) < 1e-4
+    z = W.make_noise((2, 2, 1, 16000), seed=7)
+    y = purify.ddpm_purify(hp, eps_fn, x, 2, z)
+    out = resnext.forward(csd, mel.log_mel(y))
+    assert rel_l2(out, g["logits"]) < 1e-4
+    assert np.array_equal(out.argmax(1).numpy(), g["logits"].argmax(1))
+
+
+def test_smooth_predict_counts(golden, hp, eps_fn):
+    g = golden("smooth.npz")
+    csd = resnext.make_state_dict(4321)
+    x = W.make_waveforms(1, 16000, seed=0)[0]
+    z = W.make_noise((6, 1, 16000), seed=int(g["z_seed"]))
+    sigma = float(g["sigma"])
+    assert schedule.compute_t_star(hp["Alpha_bar"], sigma)[1] == int(g["t_star"])
+    logits = torch.cat([certify.smooth_logits(hp, eps_fn, mel.log_mel, lambda s: resnext.forward(csd, s), x, z[s:s + 4], sigma)
+                        for s in (0, 4)], 0)
+    assert rel_l2(logits, g["logits"]) < 1e-4
+    counts = certify.vote_counts(logits, 10)
+    assert counts.dtype == torch.int64
+    assert np.array_equal(counts.numpy(), g["counts"])  # integer work: bit-exact
+
+
+def test_clopper_pearson_known_answers():
+    # textbook Clopper-Pearson values: k=n gives alpha**(1/n); k=0 gives 0
+    assert certify.lower_conf_bound(0, 100, 0.001) == 0.0
+    assert abs(certify.lower_conf_bound(100, 100, 0.001) - 0.001 ** (1 / 100)) < 1e-12
+    p = certify.lower_conf_bound(9900, 10000, 0.001)
+    assert 0.98 < p < 0.99
+    c0 = torch.tensor([1, 99, 0, 0, 0, 0, 0, 0, 0, 0])
+    c = torch.tensor([50, 9950, 0, 0, 0, 0, 0, 0, 0, 0])
+    cls, r = certify.certify_from_counts(c0, c, 10000, 0.25)
+    assert cls == 1 and r > 0.5
+    cls, r = certify.certify_from_counts(c0, torch.tensor([5000, 5000, 0, 0, 0, 0, 0, 0, 0, 0]), 10000, 0.25)
+    assert (cls, r) == (-1, 0.0)

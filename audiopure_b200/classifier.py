@@ -1,0 +1,79 @@
+"""ResNeXt-29 8x64 Speech-Commands classifier -- the *consumer* of the purification path.
+
+Not accelerated here (< 1 % of the path's FLOPs; it stays a cuDNN
+``nn.Module``), but the package needs the architecture to compose and benchmark the full
+purify -> log-mel -> classify step without the reference checkout.  Same layer names as
+``audio_models/ConvNets_SpeechCommands/models/resnext.py`` so its checkpoints' state dicts load.
+"""
+
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import init
+
+__all__ = ["CifarResNeXt"]
+
+
+class ResNeXtBottleneck(nn.Module):
+    """resnext.py:23-64 (type-C bottleneck: 1x1 reduce, grouped 3x3, 1x1 expand, projection shortcut)."""
+
+    def __init__(self, in_channels, out_channels, stride, cardinality, base_width, widen_factor):
+        super().__init__()
+        width_ratio = out_channels / (widen_factor * 64.0)
+        D = cardinality * int(base_width * width_ratio)
+        self.conv_reduce = nn.Conv2d(in_channels, D, 1, 1, 0, bias=False)
+        self.bn_reduce = nn.BatchNorm2d(D)
+        self.conv_conv = nn.Conv2d(D, D, 3, stride, 1, groups=cardinality, bias=False)
+        self.bn = nn.BatchNorm2d(D)
+        self.conv_expand = nn.Conv2d(D, out_channels, 1, 1, 0, bias=False)
+        self.bn_expand = nn.BatchNorm2d(out_channels)
+        self.shortcut = nn.Sequential()
+        if in_channels != out_channels:
+            self.shortcut.add_module("shortcut_conv", nn.Conv2d(in_channels, out_channels, 1, stride, 0, bias=False))
+            self.shortcut.add_module("shortcut_bn", nn.BatchNorm2d(out_channels))
+
+    def forward(self, x):
+        y = F.relu(self.bn_reduce(self.conv_reduce(x)), inplace=True)
+        y = F.relu(self.bn(self.conv_conv(y)), inplace=True)
+        y = self.bn_expand(self.conv_expand(y))
+        return F.relu(self.shortcut(x) + y, inplace=True)
+
+
+class CifarResNeXt(nn.Module):
+    """resnext.py:67-142: (B, in_channels, 32, 32) -> (B, nlabels)."""
+
+    def __init__(self, nlabels, cardinality=8, depth=29, base_width=64, widen_factor=4, in_channels=3):
+        super().__init__()
+        self.cardinality, self.depth, self.base_width, self.widen_factor = cardinality, depth, base_width, widen_factor
+        self.block_depth = (depth - 2) // 9
+        self.nlabels = nlabels
+        self.stages = [64, 64 * widen_factor, 128 * widen_factor, 256 * widen_factor]
+        self.conv_1_3x3 = nn.Conv2d(in_channels, 64, 3, 1, 1, bias=False)
+        self.bn_1 = nn.BatchNorm2d(64)
+        self.stage_1 = self._stage("stage_1", self.stages[0], self.stages[1], 1)
+        self.stage_2 = self._stage("stage_2", self.stages[1], self.stages[2], 2)
+        self.stage_3 = self._stage("stage_3", self.stages[2], self.stages[3], 2)
+        self.classifier = nn.Linear(self.stages[3], nlabels)
+        init.kaiming_normal_(self.classifier.weight)
+        for key, value in self.state_dict().items():
+            leaf = key.split(".")[-1]
+            if leaf == "weight":
+                if "conv" in key:
+                    init.kaiming_normal_(value, mode="fan_out")
+                if "bn" in key:
+                    value[...] = 1
+            elif leaf == "bias":
+                value[...] = 0
+
+    def _stage(self, name, cin, cout, stride):
+        block = nn.Sequential()
+        for j in range(self.block_depth):
+            block.add_module("%s_bottleneck_%d" % (name, j),
+                             ResNeXtBottleneck(cin if j == 0 else cout, cout, stride if j == 0 else 1,
+                                               self.cardinality, self.base_width, self.widen_factor))
+        return block
+
+    def forward(self, x):
+        x = F.relu(self.bn_1(self.conv_1_3x3(x)), inplace=True)
+        x = self.stage_3(self.stage_2(self.stage_1(x)))
+        x = F.avg_pool2d(x, 8, 1)
+        return self.classifier(x.view(-1, self.stages[3]))

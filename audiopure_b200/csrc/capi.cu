@@ -1,0 +1,615 @@
+// C ABI of audiopure_b200 (see include/audiopure_b200.h).  Host-side launch logic only: tensor-map
+// construction, workspace carving, the per-step launch sequence, the purifier loops and the NCCL shim.
+#include "../../include/audiopure_b200.h"
+
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "diffwave_kernels.cuh"
+#include "mel_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+
+#define AP_CUDA(expr)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" +        \
+                  std::to_string(__LINE__) + ")");                                                     \
+  } while (0)
+
+#define AP_CHECK(cond, msg)         \
+  do {                              \
+    if (!(cond)) return fail(msg);  \
+  } while (0)
+
+// ------------------------------------------------------------------ tensor maps (driver entry point) --
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, innermost dim contiguous, box = {64 elements (128 B), box1, 1, ...}, 128-byte swizzle,
+// out-of-bounds elements read as zero.
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, uint32_t box1) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  AP_CHECK(fn, "cuTensorMapEncodeTiled entry point not available from the driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[4];
+  cuuint32_t box[5], estr[5];
+  uint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    stride *= dims[i];
+    if (i < rank - 1) gstride[i] = stride;
+    box[i] = (i == 0) ? 64 : (i == 1 ? box1 : 1);
+    estr[i] = 1;
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+  return 0;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct ap_net {
+  int layers = 0, cycle = 0, T = 0, max_chunk = 64;
+  ap_weights w{};
+  std::vector<float> alpha, alpha_bar, sigma, sde_beta, sde_acp;
+  CUtensorMap tm_w1, tm_w2, tm_ws, tm_wf;
+  int num_sms = 0, device = 0;
+  // activation maps, rebuilt when (workspace, Bc, L) changes
+  const void* cached_ws = nullptr;
+  int cached_B = 0, cached_L = 0;
+  CUtensorMap tm_h[2], tm_gate;
+  // measurement hook (ap_profile_*)
+  bool profile = false;
+  struct Span {
+    cudaEvent_t a, b;
+    int kind;
+  };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t take_event() {
+    cudaEvent_t e = nullptr;
+    if (!pool.empty()) {
+      e = pool.back();
+      pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+  ~ap_net() {
+    for (auto& s : spans) {
+      cudaEventDestroy(s.a);
+      cudaEventDestroy(s.b);
+    }
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
+namespace {
+// Brackets one kernel launch with events when profiling is on.
+struct ProfSpan {
+  ap_net* n;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  int kind;
+  ProfSpan(ap_net* n_, cudaStream_t st_, int kind_) : n(n_), st(st_), kind(kind_) {
+    if (!n->profile || n->spans.size() > (1u << 20)) return;
+    cudaEvent_t a = n->take_event();
+    b = n->take_event();
+    cudaEventRecord(a, st);
+    n->spans.push_back({a, b, kind});
+  }
+  ~ProfSpan() {
+    if (b) cudaEventRecord(b, st);
+  }
+};
+}  // namespace
+
+namespace {
+
+struct WsLayout {
+  size_t h_bytes, off_h[2], off_gate, off_x[2], total;
+};
+
+WsLayout ws_layout(const ap_net* n, int Bc, int L) {
+  WsLayout w;
+  w.h_bytes = align_up(static_cast<size_t>(Bc) * L * ap::kC * 2, 1024);
+  w.off_h[0] = 0;
+  w.off_h[1] = w.h_bytes;
+  w.off_gate = 2 * w.h_bytes;
+  const size_t xb = align_up(static_cast<size_t>(Bc) * L * 4, 1024);
+  w.off_x[0] = w.off_gate + static_cast<size_t>(n->layers) * w.h_bytes;
+  w.off_x[1] = w.off_x[0] + xb;
+  w.total = w.off_x[1] + xb;
+  return w;
+}
+
+int ensure_maps(ap_net* n, uint8_t* ws, int Bc, int L) {
+  if (n->cached_ws == ws && n->cached_B == Bc && n->cached_L == L) return 0;
+  const WsLayout w = ws_layout(n, Bc, L);
+  const uint64_t d3[3] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc)};
+  for (int i = 0; i < 2; ++i)
+    if (make_map(&n->tm_h[i], ws + w.off_h[i], 3, d3, ap::kTileT)) return 1;
+  const uint64_t d4[4] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc),
+                          static_cast<uint64_t>(n->layers)};
+  // gate[layer] slabs are h_bytes apart; h_bytes == Bc*L*512 whenever that is a multiple of 1024
+  if (w.h_bytes != static_cast<size_t>(Bc) * L * ap::kC * 2)
+    return fail("internal: B*L must be even so that layer slabs are contiguous");
+  if (make_map(&n->tm_gate, ws + w.off_gate, 4, d4, ap::kTileT)) return 1;
+  n->cached_ws = ws;
+  n->cached_B = Bc;
+  n->cached_L = L;
+  return 0;
+}
+
+// One epsilon-network evaluation of Bc clips (+ the fused output update described by `tail`).
+int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail, uint8_t* ws, cudaStream_t st) {
+  AP_CHECK(t >= 0 && t < n->T, "diffusion step t out of range [0, T)");
+  if (ensure_maps(n, ws, Bc, L)) return 1;
+  const WsLayout w = ws_layout(n, Bc, L);
+  __nv_bfloat16* h[2] = {reinterpret_cast<__nv_bfloat16*>(ws + w.off_h[0]),
+                         reinterpret_cast<__nv_bfloat16*>(ws + w.off_h[1])};
+  const long long rows = static_cast<long long>(Bc) * L;
+  {
+    long long blocks = (rows + 7) / 8;
+    const long long cap = static_cast<long long>(n->num_sms) * 16;
+    if (blocks > cap) blocks = cap;
+    ProfSpan span(n, st, 2);
+    ap::prologue_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->w.w0, n->w.b0,
+                                                                        n->w.part0 + static_cast<size_t>(t) * ap::kC,
+                                                                        h[0], rows);
+  }
+  const int tiles_per_clip = (L + ap::kTileT - 1) / ap::kTileT;
+  const int num_tiles = tiles_per_clip * Bc;
+  const int grid = num_tiles < n->num_sms ? num_tiles : n->num_sms;
+  for (int l = 0; l < n->layers; ++l) {
+    ap::LayerArgs a;
+    a.b1 = n->w.b1 + static_cast<size_t>(l) * 512;
+    a.c2 = n->w.c2 + (static_cast<size_t>(t) * n->layers + l) * ap::kC;
+    a.h_in = h[l & 1];
+    a.h_out = h[(l + 1) & 1];
+    a.B = Bc;
+    a.L = L;
+    a.tiles_per_clip = tiles_per_clip;
+    a.num_tiles = num_tiles;
+    a.dilation = 1 << (l % n->cycle);
+    a.layer = l;
+    a.write_h = (l + 1 < n->layers) ? 1 : 0;
+    ProfSpan span(n, st, 0);
+    ap::layer_kernel<<<grid, ap::kThreads, ap::kLayerSmem, st>>>(n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate, a);
+  }
+  tail.bs = n->w.bs;
+  tail.bf = n->w.bf;
+  tail.wo = n->w.wo;
+  tail.bo = n->w.bo;
+  tail.B = Bc;
+  tail.L = L;
+  tail.tiles_per_clip = tiles_per_clip;
+  tail.num_tiles = num_tiles;
+  tail.num_layers = n->layers;
+  {
+    ProfSpan span(n, st, 1);
+    ap::tail_kernel<<<grid, ap::kThreads, ap::kTailSmem, st>>>(n->tm_gate, n->tm_ws, n->tm_wf, tail);
+  }
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+ap::TailArgs tail_update(const float* x_in, float* x_out, float ca, float cb, float cc, const float* z,
+                         uint64_t seed, uint32_t stream_id, long long elem_offset) {
+  ap::TailArgs t{};
+  t.x_in = x_in;
+  t.x_out = x_out;
+  t.eps_out = nullptr;
+  t.z = z;
+  t.ca = ca;
+  t.cb = cb;
+  t.cc = cc;
+  t.seed = seed;
+  t.stream_lo = stream_id;
+  t.elem_offset = elem_offset;
+  return t;
+}
+
+int launch_axpbz(const float* x, const float* z, float* y, float ca, float cb, long long n, uint64_t seed,
+                 uint32_t stream_id, long long elem_offset, int num_sms, cudaStream_t st) {
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (blocks > cap) blocks = cap;
+  ap::axpbz_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, z, y, ca, cb, n, seed, stream_id, elem_offset);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int check_call(const ap_net* n, int B, int L, const void* ws, size_t ws_bytes) {
+  AP_CHECK(n, "null handle");
+  AP_CHECK(B > 0 && L > 0, "B and L must be positive");
+  AP_CHECK(L % 2 == 0, "L must be even");
+  AP_CHECK(ws, "null workspace");
+  AP_CHECK(reinterpret_cast<uintptr_t>(ws) % 1024 == 0, "workspace must be 1024-byte aligned");
+  AP_CHECK(ws_bytes >= ap_workspace_bytes(n, B, L), "workspace too small: see ap_workspace_bytes");
+  return 0;
+}
+
+// Purifier loop shared by DDPM and SDE: diffuse, then `steps` fused eval+update launches per chunk.
+struct StepCoef {
+  float ca, cb, cc;
+  int t;
+};
+
+int purify_loop(ap_net* n, const float* x_in, float* x_out, int B, int L, float diff_a, float diff_b,
+                const std::vector<StepCoef>& steps, const float* z, uint64_t seed, int64_t clip_offset, uint8_t* ws,
+                cudaStream_t st) {
+  const size_t BL = static_cast<size_t>(B) * L;
+  for (int c0 = 0; c0 < B; c0 += n->max_chunk) {
+    const int Bc = (B - c0) < n->max_chunk ? (B - c0) : n->max_chunk;
+    const WsLayout w = ws_layout(n, Bc, L);
+    float* xb[2] = {reinterpret_cast<float*>(ws + w.off_x[0]), reinterpret_cast<float*>(ws + w.off_x[1])};
+    const size_t off = static_cast<size_t>(c0) * L;
+    const long long elem_off = (clip_offset + c0) * static_cast<long long>(L);
+    if (launch_axpbz(x_in + off, z ? z + off : nullptr, xb[0], diff_a, diff_b, static_cast<long long>(Bc) * L, seed,
+                     0u, elem_off, n->num_sms, st))
+      return 1;
+    int cur = 0;
+    for (size_t i = 0; i < steps.size(); ++i) {
+      const bool last = (i + 1 == steps.size());
+      float* dst = last ? x_out + off : xb[cur ^ 1];
+      const float* zi = (z && steps[i].cc != 0.f) ? z + (i + 1) * BL + off : nullptr;
+      ap::TailArgs tail = tail_update(xb[cur], dst, steps[i].ca, steps[i].cb, steps[i].cc, zi, seed,
+                                      static_cast<uint32_t>(i + 1), elem_off);
+      if (run_eval(n, xb[cur], Bc, L, steps[i].t, tail, ws, st)) return 1;
+      cur ^= 1;
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ap_last_error(void) { return g_err.c_str(); }
+int ap_abi_version(void) { return AP_ABI_VERSION; }
+
+int ap_create(const ap_config* cfg, const ap_weights* w, ap_net** out) {
+  AP_CHECK(cfg && w && out, "null argument");
+  AP_CHECK(cfg->num_res_layers > 0 && cfg->num_res_layers <= 256, "num_res_layers out of range");
+  AP_CHECK(cfg->dilation_cycle > 0 && cfg->dilation_cycle <= 16, "dilation_cycle out of range");
+  AP_CHECK(cfg->T > 0, "T must be positive");
+  AP_CHECK(cfg->alpha && cfg->alpha_bar && cfg->sigma && cfg->sde_beta && cfg->sde_alphas_cumprod,
+           "schedule tables missing");
+  int dev = 0;
+  AP_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  AP_CUDA(cudaGetDeviceProperties(&prop, dev));
+  AP_CHECK(prop.major == 10, std::string("audiopure_b200 needs an sm_100 device, found sm_") +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+  ap_net* n = new ap_net();
+  n->layers = cfg->num_res_layers;
+  n->cycle = cfg->dilation_cycle;
+  n->T = cfg->T;
+  n->max_chunk = cfg->max_chunk > 0 ? cfg->max_chunk : 64;
+  n->w = *w;
+  n->alpha.assign(cfg->alpha, cfg->alpha + cfg->T);
+  n->alpha_bar.assign(cfg->alpha_bar, cfg->alpha_bar + cfg->T);
+  n->sigma.assign(cfg->sigma, cfg->sigma + cfg->T);
+  n->sde_beta.assign(cfg->sde_beta, cfg->sde_beta + cfg->T);
+  n->sde_acp.assign(cfg->sde_alphas_cumprod, cfg->sde_alphas_cumprod + cfg->T);
+  n->num_sms = prop.multiProcessorCount;
+  n->device = dev;
+  const uint64_t L = static_cast<uint64_t>(n->layers);
+  const uint64_t dw1[2] = {768, L * 512}, dw2[2] = {256, L * 256}, dws[2] = {L * 256, 256}, dwf[2] = {256, 256};
+  int rc = make_map(&n->tm_w1, w->w1, 2, dw1, 256) || make_map(&n->tm_w2, w->w2, 2, dw2, 256) ||
+           make_map(&n->tm_ws, w->ws, 2, dws, 256) || make_map(&n->tm_wf, w->wf, 2, dwf, 256);
+  if (rc) {
+    delete n;
+    return 1;
+  }
+  cudaError_t e1 = cudaFuncSetAttribute(ap::layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::kLayerSmem);
+  cudaError_t e2 = cudaFuncSetAttribute(ap::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::kTailSmem);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    delete n;
+    return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") +
+                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  *out = n;
+  return 0;
+}
+
+void ap_destroy(ap_net* net) { delete net; }
+
+size_t ap_workspace_bytes(const ap_net* net, int B, int L) {
+  if (!net || B <= 0 || L <= 0) return 0;
+  const int Bc = B < net->max_chunk ? B : net->max_chunk;
+  return ws_layout(net, Bc, L).total;
+}
+
+int ap_eps(ap_net* net, const float* x, int B, int L, int t, float* eps_out, void* ws, size_t ws_bytes,
+           void* stream) {
+  if (check_call(net, B, L, ws, ws_bytes)) return 1;
+  AP_CHECK(x && eps_out, "null tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < B; c0 += net->max_chunk) {
+    const int Bc = (B - c0) < net->max_chunk ? (B - c0) : net->max_chunk;
+    ap::TailArgs tail{};
+    tail.x_in = x + static_cast<size_t>(c0) * L;
+    tail.eps_out = eps_out + static_cast<size_t>(c0) * L;
+    if (run_eval(net, x + static_cast<size_t>(c0) * L, Bc, L, t, tail, static_cast<uint8_t*>(ws), st)) return 1;
+  }
+  return 0;
+}
+
+int ap_step(ap_net* net, const float* x_in, float* x_out, int B, int L, int t, float ca, float cb, float cc,
+            const float* z, uint64_t seed, uint32_t stream_id, int64_t clip_offset, void* ws, size_t ws_bytes,
+            void* stream) {
+  if (check_call(net, B, L, ws, ws_bytes)) return 1;
+  AP_CHECK(x_in && x_out, "null tensor");
+  AP_CHECK(x_in != x_out, "ap_step is not in-place");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < B; c0 += net->max_chunk) {
+    const int Bc = (B - c0) < net->max_chunk ? (B - c0) : net->max_chunk;
+    const size_t off = static_cast<size_t>(c0) * L;
+    ap::TailArgs tail = tail_update(x_in + off, x_out + off, ca, cb, cc, z ? z + off : nullptr, seed, stream_id,
+                                    (clip_offset + c0) * static_cast<long long>(L));
+    if (run_eval(net, x_in + off, Bc, L, t, tail, static_cast<uint8_t*>(ws), st)) return 1;
+  }
+  return 0;
+}
+
+int ap_ddpm_purify(ap_net* net, const float* x_in, float* x_out, int B, int L, int t_star, const float* z,
+                   uint64_t seed, int64_t clip_offset, void* ws, size_t ws_bytes, void* stream) {
+  if (check_call(net, B, L, ws, ws_bytes)) return 1;
+  AP_CHECK(x_in && x_out, "null tensor");
+  AP_CHECK(t_star >= 1 && t_star <= net->T, "t_star out of range [1, T]");
+  // diffwave_ddpm.py:67 and :159-160, in double from the reference-built fp32 tables
+  const double ab = net->alpha_bar[t_star - 1];
+  std::vector<StepCoef> steps;
+  for (int t = t_star - 1; t >= 0; --t) {
+    const double al = net->alpha[t], abt = net->alpha_bar[t];
+    StepCoef s;
+    s.t = t;
+    s.ca = static_cast<float>(1.0 / std::sqrt(al));
+    s.cb = static_cast<float>(-(1.0 - al) / std::sqrt(1.0 - abt) / std::sqrt(al));
+    s.cc = t > 0 ? net->sigma[t] : 0.f;
+    steps.push_back(s);
+  }
+  return purify_loop(net, x_in, x_out, B, L, static_cast<float>(std::sqrt(ab)), static_cast<float>(std::sqrt(1.0 - ab)),
+                     steps, z, seed, clip_offset, static_cast<uint8_t*>(ws), static_cast<cudaStream_t>(stream));
+}
+
+int ap_sde_purify(ap_net* net, const float* x_in, float* x_out, int B, int L, int t, const float* z, uint64_t seed,
+                  int64_t clip_offset, void* ws, size_t ws_bytes, void* stream) {
+  if (check_call(net, B, L, ws, ws_bytes)) return 1;
+  AP_CHECK(x_in && x_out, "null tensor");
+  AP_CHECK(t >= 1 && t <= net->T, "t out of range [1, T]");
+  // diffwave_sde.py:190-191 (diffusion) and :73-134 with dt = 1/N (one Euler-Maruyama step at index k):
+  //   x <- (1 + beta_k/2) x - beta_k / sqrt(1 - abar_k) eps + sqrt(beta_k) sqrt((1-abar_{k-1})/(1-abar_k)) z
+  const double ab = net->sde_acp[t - 1];
+  std::vector<StepCoef> steps;
+  for (int k = t - 1; k >= 0; --k) {
+    const double bk = net->sde_beta[k], ak = net->sde_acp[k];
+    StepCoef s;
+    s.t = k;
+    s.ca = static_cast<float>(1.0 + 0.5 * bk);
+    s.cb = static_cast<float>(-bk / std::sqrt(1.0 - ak));
+    s.cc = k > 0 ? static_cast<float>(std::sqrt(bk) * std::sqrt(1.0 - net->sde_acp[k - 1]) / std::sqrt(1.0 - ak)) : 0.f;
+    steps.push_back(s);
+  }
+  return purify_loop(net, x_in, x_out, B, L, static_cast<float>(std::sqrt(ab)), static_cast<float>(std::sqrt(1.0 - ab)),
+                     steps, z, seed, clip_offset, static_cast<uint8_t*>(ws), static_cast<cudaStream_t>(stream));
+}
+
+int ap_one_shot(ap_net* net, const float* x_in, float* x_out, int B, int L, int reverse_timestep, void* ws,
+                size_t ws_bytes, void* stream) {
+  AP_CHECK(net, "null handle");
+  AP_CHECK(reverse_timestep >= 1 && reverse_timestep <= net->T, "reverse_timestep out of range [1, T]");
+  const int t = reverse_timestep - 1;
+  const double ab = net->alpha_bar[t];  // diffwave_ddpm.py:195-205
+  return ap_step(net, x_in, x_out, B, L, t, static_cast<float>(std::sqrt(1.0 / ab)),
+                 static_cast<float>(-std::sqrt(1.0 / ab - 1.0)), 0.f, nullptr, 0, 0, 0, ws, ws_bytes, stream);
+}
+
+int ap_logmel(const float* x, int B, int L, float* out, const ap_mel_tables* tabs, void* stream) {
+  AP_CHECK(x && out && tabs, "null argument");
+  AP_CHECK(B > 0 && L > 0, "B and L must be positive");
+  AP_CHECK(tabs->n_mels > 0 && tabs->n_mels <= 128, "n_mels out of range");
+  ap::MelArgs a;
+  a.x = x;
+  a.out = out;
+  a.tw = static_cast<const float2*>(tabs->twiddles);
+  a.fb_start = tabs->fb_start;
+  a.fb_len = tabs->fb_len;
+  a.fb_off = tabs->fb_off;
+  a.fb_w = tabs->fb_w;
+  a.B = B;
+  a.L = L;
+  a.n_frames = 1 + L / ap::kHop;
+  a.n_mels = tabs->n_mels;
+  const int pairs = (a.n_frames + 1) / 2;
+  ap::logmel_kernel<<<B * pairs, ap::kMelThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ap_smooth_inputs(const float* x, int L, int n_draws, float sigma, float scale, const float* z, uint64_t seed,
+                     uint32_t clip, int64_t first_draw, float* out, void* stream) {
+  AP_CHECK(x && out, "null tensor");
+  AP_CHECK(L > 0 && n_draws > 0, "L and n_draws must be positive");
+  const long long n = static_cast<long long>(n_draws) * L;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ap::smooth_inputs_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, z, out, L, n_draws, sigma, scale, seed, clip, first_draw);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ap_vote_counts(const float* logits, int rows, int K, int64_t* counts, void* stream) {
+  AP_CHECK(logits && counts, "null tensor");
+  AP_CHECK(rows > 0 && K > 0, "rows and K must be positive");
+  int blocks = (rows + 255) / 256;
+  if (blocks > 148) blocks = 148;
+  ap::vote_counts_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, rows, K, reinterpret_cast<unsigned long long*>(counts));
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ap_profile_enable(ap_net* net, int enable) {
+  AP_CHECK(net, "null handle");
+  net->profile = enable != 0;
+  return 0;
+}
+
+int ap_profile_read(ap_net* net, double ms_sum[3], int64_t launches[3]) {
+  AP_CHECK(net && ms_sum && launches, "null argument");
+  for (auto& s : net->spans) {
+    AP_CUDA(cudaEventSynchronize(s.b));
+    float ms = 0.f;
+    AP_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+    ms_sum[s.kind] += ms;
+    launches[s.kind] += 1;
+    net->pool.push_back(s.a);
+    net->pool.push_back(s.b);
+  }
+  net->spans.clear();
+  return 0;
+}
+
+int ap_debug_gemm(const void* a_bf16, const void* b_bf16, float* d, int K, void* stream) {
+  AP_CHECK(a_bf16 && b_bf16 && d, "null tensor");
+  AP_CHECK(K > 0 && K % 64 == 0, "K must be a positive multiple of 64");
+  CUtensorMap ta, tb;
+  const uint64_t da[2] = {static_cast<uint64_t>(K), 128}, db[2] = {static_cast<uint64_t>(K), 256};
+  if (make_map(&ta, a_bf16, 2, da, 128) || make_map(&tb, b_bf16, 2, db, 256)) return 1;
+  const int smem = ap::kStageBytes + 64 + 1024;
+  AP_CUDA(cudaFuncSetAttribute(ap::debug_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ap::debug_gemm_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, d, K);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ NCCL (dlopen) --
+struct ap_comm {
+  void* comm = nullptr;
+};
+
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, ...) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId {
+  char internal[128];
+};
+typedef int (*CommInitRankFn)(void**, int, NcclId, int);
+
+NcclApi* nccl() {
+  static NcclApi api;
+  if (api.lib) return &api;
+  const char* env = getenv("AP_NCCL_LIB");
+  const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm) continue;
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return nullptr;
+  api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<int (*)(void**, int, ...)>(dlsym(api.lib, "ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
+      dlsym(api.lib, "ncclAllReduce"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+    dlclose(api.lib);
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+int nccl_fail(NcclApi* n, const char* what, int rc) {
+  return fail(std::string(what) + ": " + (n->GetErrorString ? n->GetErrorString(rc) : "NCCL error") + " (" +
+              std::to_string(rc) + ")");
+}
+}  // namespace
+
+int ap_comm_unique_id(uint8_t id[AP_COMM_ID_BYTES]) {
+  NcclApi* n = nccl();
+  AP_CHECK(n, "libnccl.so.2 could not be loaded (set AP_NCCL_LIB)");
+  NcclId nid;
+  int rc = n->GetUniqueId(&nid);
+  if (rc) return nccl_fail(n, "ncclGetUniqueId", rc);
+  memcpy(id, nid.internal, AP_COMM_ID_BYTES);
+  return 0;
+}
+
+int ap_comm_init(int rank, int world, const uint8_t id[AP_COMM_ID_BYTES], ap_comm** out) {
+  NcclApi* n = nccl();
+  AP_CHECK(n, "libnccl.so.2 could not be loaded (set AP_NCCL_LIB)");
+  AP_CHECK(out && world > 0 && rank >= 0 && rank < world, "bad rank/world");
+  NcclId nid;
+  memcpy(nid.internal, id, AP_COMM_ID_BYTES);
+  ap_comm* c = new ap_comm();
+  int rc = reinterpret_cast<CommInitRankFn>(n->CommInitRank)(&c->comm, world, nid, rank);
+  if (rc) {
+    delete c;
+    return nccl_fail(n, "ncclCommInitRank", rc);
+  }
+  *out = c;
+  return 0;
+}
+
+int ap_allreduce_counts(ap_comm* comm, int64_t* counts, size_t cnt, void* stream) {
+  NcclApi* n = nccl();
+  AP_CHECK(n && comm && comm->comm, "communicator not initialised");
+  const int kNcclInt64 = 4, kNcclSum = 0;
+  int rc = n->AllReduce(counts, counts, cnt, kNcclInt64, kNcclSum, comm->comm, static_cast<cudaStream_t>(stream));
+  if (rc) return nccl_fail(n, "ncclAllReduce", rc);
+  return 0;
+}
+
+void ap_comm_destroy(ap_comm* comm) {
+  if (!comm) return;
+  NcclApi* n = nccl();
+  if (n && comm->comm) n->CommDestroy(comm->comm);
+  delete comm;
+}
+
+}  // extern "C"

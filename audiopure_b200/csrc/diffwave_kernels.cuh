@@ -1,0 +1,712 @@
+// DiffWave epsilon-network kernels for sm_100a.
+//
+// Data layout in HBM:
+//   h      : [B][L][256] bf16, channels-last -- a time step is one 512-byte row, so every conv tap of a
+//            128-step tile is one TMA box at row offset l0 + (tap-1)*dilation; the 3-D tensor map (c, l, b)
+//            zero-fills rows outside [0, L), which IS the conv's zero padding and keeps taps from bleeding
+//            across clips.  h_n already contains the "+ fc_t(emb)" shift of layer n (WaveNet.py:82-84).
+//   gate   : [layers][B][L][256] bf16 -- tanh*sigmoid output of every layer, kept so that the 36 skip
+//            projections become ONE K = layers*256 GEMM in the tail kernel (fp32 accumulation in TMEM)
+//            instead of a 16 MB/clip fp32 read-modify-write per layer.
+//
+// Orientation of every GEMM: M = 128 time steps (TMEM lanes), N = 256 output channels (TMEM columns),
+// K = input channels (x taps).  A = activations, B = weights, both K-major, 128-byte swizzle.
+#pragma once
+
+#include "sm100.cuh"
+
+namespace ap {
+
+constexpr int kC = 256;          // residual / skip / gate channels (the only width the kernels support)
+constexpr int kTileT = 128;      // time steps per tile = UMMA M
+constexpr int kStages = 3;       // TMA -> MMA ring depth
+constexpr uint32_t kABytes = kTileT * 128;  // [128 rows x 64 bf16]
+constexpr uint32_t kBBytes = 256 * 128;     // [256 rows x 64 bf16]
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kTileBytes = kTileT * kC * 2;  // a full [128 x 256] bf16 operand tile (4 swizzled sub-tiles)
+constexpr int kThreads = 384;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-3: idle, warps 4-11: epilogue
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr float kSqrtHalf = 0.70710678118654752440f;
+
+constexpr uint32_t kLayerSmem = kStages * kStageBytes + kTileBytes + 512 * 4 + 256 * 4 + 16 * 8 + 16 + 1024;
+constexpr uint32_t kTailSmem = kStages * kStageBytes + kTileBytes + 3 * 256 * 4 + 2 * 2 * 128 * 4 + 16 * 8 + 16 + 1024;
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10, counter-based: noise is a pure function of (seed, stream, element index), so how a batch
+// is sharded over GPUs or chunked over launches never changes it.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, uint32_t (&out)[4]) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = static_cast<uint32_t>(p0);
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Standard normal for element `idx` of stream (stream_hi, stream_lo) under `seed` (Box-Muller on one
+// Philox block per 4 consecutive elements).
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream_lo, uint32_t stream_hi, uint64_t idx) {
+  uint32_t r[4];
+  const uint64_t blk = idx >> 2;
+  philox4x32_10(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), stream_lo, stream_hi,
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const int sel = static_cast<int>(idx & 3);
+  const uint32_t a = r[(sel >> 1) * 2], b = r[(sel >> 1) * 2 + 1];
+  const float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+  const float u2 = static_cast<float>(b >> 8) * (1.0f / 16777216.0f);           // [0, 1)
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return rad * ((sel & 1) ? s : c);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K0: init conv (1 -> 256, k = 1, weight-norm folded) + ReLU + layer-0 step shift, fp32 [B][L] -> bf16
+// [B][L][256].  WaveNet.py:147,168 then :82-84 of block 0.  HBM-bound: 4 B in, 512 B out per time step.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prologue_kernel(const float* __restrict__ x, const float* __restrict__ w0,
+                                                       const float* __restrict__ b0,
+                                                       const float* __restrict__ part0,
+                                                       __nv_bfloat16* __restrict__ h, long long rows) {
+  const int cg = threadIdx.x & 31;  // this thread's 8 channels
+  float w[8], b[8], p[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    w[j] = w0[cg * 8 + j];
+    b[j] = b0[cg * 8 + j];
+    p[j] = part0[cg * 8 + j];
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += stride) {
+    const float xv = __ldg(x + row);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = fmaxf(fmaf(w[2 * j], xv, b[2 * j]), 0.f) + p[2 * j];
+      const float v1 = fmaxf(fmaf(w[2 * j + 1], xv, b[2 * j + 1]), 0.f) + p[2 * j + 1];
+      ow[j] = pack_bf16x2(v0, v1);
+    }
+    reinterpret_cast<uint4*>(h + row * kC)[cg] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: one residual layer (WaveNet.py:75-97), fully fused, persistent over 128-step tiles.
+//
+//   GEMM1  D1[128 x 512] = sum_{tap,c} h[l + (tap-1)d][c] * W1[o][c][tap]     (K = 768)
+//          issued as two N = 256 chunks; chunk c holds gate channels [128c, 128c+128): TMEM columns
+//          [0,128) are their tanh rows, [128,256) their sigmoid rows (W1 rows are permuted at pack time).
+//   gate   g = tanh(D1t + b) * sigmoid(D1s + b)  -> bf16 -> shared memory (K-major, SW128) AND, by TMA
+//          store from that same shared tile, to gate[layer] in HBM for the tail's skip GEMM.
+//   GEMM2  D2[128 x 256] = g * (sqrt(.5) W_res)^T                                  (K = 256)
+//   out    h_next = sqrt(.5) * h + D2 + (sqrt(.5) b_res + part_{n+1})   (the residual term is the shifted
+//          input -- SURVEY section 0 fact 1 -- and the next layer's shift is folded in here).
+//
+// TMEM (512 columns): two 256-column buffers X, Y.  For tile parity p: chunk0 -> bufA, chunk1 -> bufB,
+// D2 -> bufA again (its gate half was drained by then), with (bufA, bufB) = (X, Y) for even tiles and
+// (Y, X) for odd tiles, so the MMA warp runs ahead of the epilogue by one chunk at all times.
+// ---------------------------------------------------------------------------------------------------
+struct LayerArgs {
+  const float* b1;             // [512] conv bias, permuted like W1's rows
+  const float* c2;             // [256] sqrt(.5)*b_res + part_{n+1}(t)
+  const __nv_bfloat16* h_in;   // [B][L][256]
+  __nv_bfloat16* h_out;        // [B][L][256]
+  int B, L, tiles_per_clip, num_tiles;
+  int dilation, layer;
+  int write_h;                 // 0 for the last layer (its residual output is never consumed)
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w1,
+             const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_gate,
+             const LayerArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* stage_base = smem;
+  uint8_t* gate_s = smem + kStages * kStageBytes;
+  float* b1s = reinterpret_cast<float*>(gate_s + kTileBytes);
+  float* c2s = b1s + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c2s + 256);
+  uint64_t* full = bars;            // [kStages] TMA -> MMA
+  uint64_t* empty = bars + 3;       // [kStages] MMA -> TMA
+  uint64_t* d1_full = bars + 6;     // [2] chunk accumulator ready        MMA -> epilogue
+  uint64_t* gate_ready = bars + 8;  // [2] gate half in smem, chunk's TMEM drained   epilogue -> MMA
+  uint64_t* d2_full = bars + 10;    //     residual accumulator ready     MMA -> epilogue
+  uint64_t* d2_empty = bars + 11;   //     residual accumulator drained   epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 512; i += kThreads) b1s[i] = a.b1[i];
+  for (int i = threadIdx.x; i < 256; i += kThreads) c2s[i] = a.c2[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&d1_full[0], 1);
+    mbar_init(&d1_full[1], 1);
+    mbar_init(&gate_ready[0], kEpiThreads / 32);
+    mbar_init(&gate_ready[1], kEpiThreads / 32);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, kEpiThreads / 32);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_h);
+    tma_prefetch_desc(&tm_w1);
+    tma_prefetch_desc(&tm_w2);
+    tma_prefetch_desc(&tm_gate);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_clip;
+        const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
+        for (int c = 0; c < 2; ++c) {
+          for (int ks = 0; ks < 12; ++ks, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 1);
+            mbar_arrive_expect_tx(&full[s], kStageBytes);
+            uint8_t* sa = stage_base + s * kStageBytes;
+            const int tap = ks >> 2;
+            tma_load_3d(sa, &tm_h, &full[s], (ks & 3) * 64, l0 + (tap - 1) * a.dilation, b);
+            tma_load_2d(sa + kABytes, &tm_w1, &full[s], ks * 64, a.layer * 512 + c * 256);
+          }
+        }
+        for (int ks = 0; ks < 4; ++ks, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 2);
+          mbar_arrive_expect_tx(&full[s], kBBytes);
+          tma_load_2d(stage_base + s * kStageBytes + kABytes, &tm_w2, &full[s], ks * 64, a.layer * 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+      uint32_t it = 0;
+      int i = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
+        const uint32_t p = i & 1;
+        const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
+        for (int c = 0; c < 2; ++c) {
+          if (c == 1 && i > 0) {  // bufB held the previous tile's residual accumulator
+            mbar_wait(d2_empty, (i - 1) & 1, 3);
+            tc_fence_after();
+          }
+          const uint32_t d = c ? bufB : bufA;
+          for (int ks = 0; ks < 12; ++ks, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&full[s], (it / kStages) & 1, 4);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + s * kStageBytes);
+            const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+            umma_commit(&empty[s]);
+          }
+          umma_commit(&d1_full[c]);
+        }
+        for (int ks = 0; ks < 4; ++ks, ++it) {
+          if (ks == 0 || ks == 2) {  // K 0..127 needs gate half 0 (and bufA drained), K 128..255 half 1
+            mbar_wait(&gate_ready[ks >> 1], p, 5);
+            tc_fence_after();
+          }
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1, 6);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(gate_s + ks * kABytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(stage_base + s * kStageBytes + kABytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(bufA, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(d2_full);
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ======================= epilogue (8 warps) =======================
+    const int e = warp - kEpiWarp0;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    const int hh = e >> 2;    // which half of the columns this warpgroup handles
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
+      const uint32_t p = i & 1;
+      const int b = tile / a.tiles_per_clip;
+      const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
+      const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
+      const bool row_ok = (l0 + row) < a.L;
+
+      // ---- gate: two chunks of 128 gate channels ----
+      for (int c = 0; c < 2; ++c) {
+        mbar_wait(&d1_full[c], p, 7);
+        tc_fence_after();
+        const uint32_t buf = (c ? bufB : bufA) + lane_addr;
+#pragma unroll 1
+        for (int itn = 0; itn < 2; ++itn) {
+          const int j0 = hh * 64 + itn * 32;  // gate channel within the chunk
+          uint32_t rt[32], rs[32];
+          tmem_ld32(buf + j0, rt);
+          tmem_ld32(buf + 128 + j0, rs);
+          tmem_ld_wait();
+          const float* bt = b1s + c * 256 + j0;
+          const float* bs = bt + 128;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float o0 = tanh_fast(__uint_as_float(rt[2 * j]) + bt[2 * j]) *
+                             sigmoid_fast(__uint_as_float(rs[2 * j]) + bs[2 * j]);
+            const float o1 = tanh_fast(__uint_as_float(rt[2 * j + 1]) + bt[2 * j + 1]) *
+                             sigmoid_fast(__uint_as_float(rs[2 * j + 1]) + bs[2 * j + 1]);
+            pk[j] = pack_bf16x2(o0, o1);
+          }
+          const int gc = c * 128 + j0;  // first gate channel of these 32
+          uint8_t* sub = gate_s + (gc >> 6) * kABytes;
+          const int q0 = (gc & 63) >> 3;
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            *reinterpret_cast<uint4*>(sub + sw128_offset(row, q0 + v)) =
+                make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gate_ready[c]);
+      }
+
+      // ---- gate tile -> HBM (operand of the tail's skip GEMM) ----
+      named_bar_sync(1, kEpiThreads);
+      if (e == 0 && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tma_store_4d(&tm_gate, gate_s + s * kABytes, s * 64, l0, b, a.layer);
+        tma_store_commit();
+      }
+
+      // ---- residual output ----
+      mbar_wait(d2_full, p, 8);
+      tc_fence_after();
+      const size_t grow = (static_cast<size_t>(b) * a.L + l0 + row) * kC;
+#pragma unroll 1
+      for (int itn = 0; itn < 4; ++itn) {
+        const int j0 = hh * 128 + itn * 32;
+        uint4 xv[4];
+        if (row_ok) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) xv[v] = __ldg(reinterpret_cast<const uint4*>(a.h_in + grow + j0) + v);
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) xv[v] = make_uint4(0, 0, 0, 0);
+        }
+        uint32_t r[32];
+        tmem_ld32(bufA + lane_addr + j0, r);
+        tmem_ld_wait();
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+        uint4 ov[4];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(ov);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float v0 = fmaf(bf16_lo(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j]) + c2s[j0 + 2 * j]);
+          const float v1 = fmaf(bf16_hi(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j + 1]) + c2s[j0 + 2 * j + 1]);
+          ow[j] = pack_bf16x2(v0, v1);
+        }
+        if (row_ok && a.write_h) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) reinterpret_cast<uint4*>(a.h_out + grow + j0)[v] = ov[v];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty);
+      // the gate tile in smem is rewritten by the next tile: its TMA store must have finished reading it
+      if (e == 0 && lane == 0) tma_store_wait_read();
+      named_bar_sync(1, kEpiThreads);
+    }
+    if (e == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: skip GEMM + output head + reverse-step update, persistent over 128-step tiles.
+//
+//   GEMMs  S[128 x 256]  = sum_n gate_n * (sqrt(1/N) W_skip,n)^T      (K = N*256; WaveNet.py:95,133,135)
+//   head   y  = relu(bf16(S + bias) * W_f^T + b_f)                     (GEMM, K = 256; WaveNet.py:160-161)
+//          eps = y . w_o + b_o                                          (256 -> 1 dot; WaveNet.py:162)
+//   update x_out = ca * x_in + cb * eps + cc * z                        (diffwave_ddpm.py:159,99-102 /
+//          diffwave_sde.py Euler-Maruyama / one-shot, as coefficients), z injected or Philox.
+//
+// TMEM: two 256-column buffers; tile i accumulates S in buffer i&1, the head GEMM of tile i overwrites the
+// same buffer once the epilogue has turned S into the bf16 smem operand, and is issued in the middle of
+// tile i+1's K loop so the tensor pipe never waits for the epilogue.
+// ---------------------------------------------------------------------------------------------------
+struct TailArgs {
+  const float* bs;      // [256] sqrt(1/N) * sum_n b_skip,n
+  const float* bf;      // [256]
+  const float* wo;      // [256]
+  float bo;
+  const float* x_in;    // [B][L]
+  const float* z;       // [B][L] injected noise or nullptr
+  float* x_out;         // [B][L] or nullptr
+  float* eps_out;       // [B][L] or nullptr
+  float ca, cb, cc;
+  unsigned long long seed;   // Philox key (used when z == nullptr and cc != 0)
+  uint32_t stream_lo;        // Philox stream: purpose/step id
+  long long elem_offset;     // global element index of x_in[0] (keeps noise independent of sharding)
+  int B, L, tiles_per_clip, num_tiles, num_layers;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__ CUtensorMap tm_ws,
+            const __grid_constant__ CUtensorMap tm_wf, const TailArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* stage_base = smem;
+  uint8_t* s_tile = smem + kStages * kStageBytes;
+  float* bss = reinterpret_cast<float*>(s_tile + kTileBytes);
+  float* bfs = bss + 256;
+  float* wos = bfs + 256;
+  float* partial = wos + 256;  // [2 parities][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(partial + 512);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 3;
+  uint64_t* d_full = bars + 6;    // [2] skip accumulator ready      MMA -> epilogue
+  uint64_t* d_empty = bars + 8;   // [2] buffer fully consumed       epilogue -> MMA
+  uint64_t* s_ready = bars + 10;  //     bf16 skip tile in smem      epilogue -> MMA
+  uint64_t* d3_full = bars + 11;  // [2] head accumulator ready      MMA -> epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 256; i += kThreads) {
+    bss[i] = a.bs[i];
+    bfs[i] = a.bf[i];
+    wos[i] = a.wo[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&d_full[s], 1);
+      mbar_init(&d_empty[s], kEpiThreads / 32);
+      mbar_init(&d3_full[s], 1);
+    }
+    mbar_init(s_ready, kEpiThreads / 32);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_gate);
+    tma_prefetch_desc(&tm_ws);
+    tma_prefetch_desc(&tm_wf);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int total_ks = a.num_layers * 4;
+  const int J = total_ks / 2 < 16 ? total_ks / 2 : 16;  // where the previous tile's head GEMM is slotted in
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int i = 0;
+      auto load_wf = [&]() {
+        for (int ks = 0; ks < 4; ++ks, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 11);
+          mbar_arrive_expect_tx(&full[s], kBBytes);
+          tma_load_2d(stage_base + s * kStageBytes + kABytes, &tm_wf, &full[s], ks * 64, 0);
+        }
+      };
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
+        const int b = tile / a.tiles_per_clip;
+        const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
+        for (int ks = 0; ks < total_ks; ++ks, ++it) {
+          if (ks == J && i > 0) load_wf();
+          const int s = it % kStages;
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 12);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          uint8_t* sa = stage_base + s * kStageBytes;
+          tma_load_4d(sa, &tm_gate, &full[s], (ks & 3) * 64, l0, b, ks >> 2);
+          tma_load_2d(sa + kABytes, &tm_ws, &full[s], ks * 64, 0);
+        }
+      }
+      if (i > 0) load_wf();
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+      uint32_t it = 0;
+      int i = 0;
+      auto head_gemm = [&](int ip) {
+        const uint32_t d = tmem_base + ((ip & 1) ? 256u : 0u);
+        mbar_wait(s_ready, ip & 1, 13);
+        tc_fence_after();
+        for (int ks = 0; ks < 4; ++ks, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1, 14);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(s_tile + ks * kABytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(stage_base + s * kStageBytes + kABytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&d3_full[ip & 1]);
+      };
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
+        const uint32_t p = i & 1, u = i >> 1;
+        const uint32_t d = tmem_base + (p ? 256u : 0u);
+        if (u >= 1) {
+          mbar_wait(&d_empty[p], (u - 1) & 1, 15);
+          tc_fence_after();
+        }
+        for (int ks = 0; ks < total_ks; ++ks, ++it) {
+          if (ks == J && i > 0) head_gemm(i - 1);
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1, 16);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + s * kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&d_full[p]);
+      }
+      if (i > 0) head_gemm(i - 1);
+    }
+  } else if (warp >= kEpiWarp0) {
+    const int e = warp - kEpiWarp0;
+    const int q = warp & 3;
+    const int hh = e >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
+      const uint32_t p = i & 1, u = i >> 1;
+      const int b = tile / a.tiles_per_clip;
+      const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
+      const uint32_t buf = tmem_base + (p ? 256u : 0u) + lane_addr;
+      const bool row_ok = (l0 + row) < a.L;
+
+      // ---- skip sum -> bf16 operand tile ----
+      mbar_wait(&d_full[p], u & 1, 17);
+      tc_fence_after();
+#pragma unroll 1
+      for (int itn = 0; itn < 4; ++itn) {
+        const int j0 = hh * 128 + itn * 32;
+        uint32_t r[32];
+        tmem_ld32(buf + j0, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + bss[j0 + 2 * j],
+                              __uint_as_float(r[2 * j + 1]) + bss[j0 + 2 * j + 1]);
+        uint8_t* sub = s_tile + (j0 >> 6) * kABytes;
+        const int q0 = (j0 & 63) >> 3;
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          *reinterpret_cast<uint4*>(sub + sw128_offset(row, q0 + v)) =
+              make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_ready);
+
+      // ---- head: relu, 256 -> 1 dot ----
+      mbar_wait(&d3_full[p], u & 1, 18);
+      tc_fence_after();
+      float acc = 0.f;
+#pragma unroll 1
+      for (int itn = 0; itn < 4; ++itn) {
+        const int j0 = hh * 128 + itn * 32;
+        uint32_t r[32];
+        tmem_ld32(buf + j0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaf(fmaxf(__uint_as_float(r[j]) + bfs[j0 + j], 0.f), wos[j0 + j], acc);
+      }
+      partial[(p * 2 + hh) * 128 + row] = acc;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_empty[p]);
+      named_bar_sync(1, kEpiThreads);
+      if (hh == 0 && row_ok) {
+        const float eps = partial[(p * 2) * 128 + row] + partial[(p * 2 + 1) * 128 + row] + a.bo;
+        const size_t idx = static_cast<size_t>(b) * a.L + l0 + row;
+        if (a.eps_out) a.eps_out[idx] = eps;
+        if (a.x_out) {
+          float v = fmaf(a.ca, a.x_in[idx], a.cb * eps);
+          if (a.cc != 0.f) {
+            const float zz = a.z ? a.z[idx]
+                                 : philox_normal(a.seed, a.stream_lo, 0u,
+                                                 static_cast<uint64_t>(a.elem_offset) + idx);
+            v = fmaf(a.cc, zz, v);
+          }
+          a.x_out[idx] = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bring-up / regression kernel: D[128 x 256] = A[128 x K] * B[256 x K]^T through exactly the TMA box,
+// swizzle, descriptor and TMEM-load conventions the two kernels above rely on.  One CTA, 128 threads.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+debug_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, float* d,
+                  int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStageBytes);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    for (int ks = 0; ks < K / 64; ++ks) {
+      mbar_arrive_expect_tx(&bars[0], kStageBytes);
+      tma_load_2d(smem, &tm_a, &bars[0], ks * 64, 0);
+      tma_load_2d(smem + kABytes, &tm_b, &bars[0], ks * 64, 0);
+      mbar_wait(&bars[0], ks & 1, 21);
+      tc_fence_after();
+      const uint64_t da = umma_desc_sw128(smem_u32(smem)), db = umma_desc_sw128(smem_u32(smem + kABytes));
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+      umma_commit(&bars[1]);
+      mbar_wait(&bars[1], ks & 1, 22);
+    }
+  }
+  __syncthreads();
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int j0 = 0; j0 < 256; j0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + j0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) d[row * 256 + j0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Small HBM-bound elementwise kernels.
+// ---------------------------------------------------------------------------------------------------
+// y = a*x + b*z ; z injected or Philox(seed, stream, elem_offset + i).  diffwave_ddpm.py:66-67, diffwave_sde.py:185-191.
+__global__ void __launch_bounds__(256) axpbz_kernel(const float* __restrict__ x, const float* __restrict__ z,
+                                                    float* __restrict__ y, float ca, float cb, long long n,
+                                                    unsigned long long seed, uint32_t stream_lo,
+                                                    long long elem_offset) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float zz = z ? z[i] : philox_normal(seed, stream_lo, 0u, static_cast<uint64_t>(elem_offset + i));
+    y[i] = fmaf(ca, x[i], cb * zz);
+  }
+}
+
+// Smoothing draws (certified_robust.py:46-54): out[j][l] = scale * (x[l] + sigma * z_j[l]) for draws
+// j in [0, n_draws); z injected ([n_draws][L]) or Philox keyed on (seed, clip, first_draw + j, l).
+__global__ void __launch_bounds__(256) smooth_inputs_kernel(const float* __restrict__ x, const float* __restrict__ z,
+                                                            float* __restrict__ out, int L, int n_draws, float sigma,
+                                                            float scale, unsigned long long seed, uint32_t clip,
+                                                            long long first_draw) {
+  const long long n = static_cast<long long>(n_draws) * L;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int l = static_cast<int>(i % L);
+    const long long j = i / L;
+    const float zz = z ? z[i]
+                       : philox_normal(seed, 0x534D4F4Fu /* 'SMOO' */, clip,
+                                       static_cast<uint64_t>(first_draw + j) * static_cast<uint64_t>(L) + l);
+    out[i] = scale * fmaf(sigma, zz, x[l]);
+  }
+}
+
+// certified_robust.py:58-67: counts[c] += #rows whose argmax is c (lowest index wins ties, like torch.max).
+__global__ void __launch_bounds__(256) vote_counts_kernel(const float* __restrict__ logits, int rows, int K,
+                                                          unsigned long long* __restrict__ counts) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const float* p = logits + static_cast<size_t>(r) * K;
+    int best = 0;
+    float bv = p[0];
+    for (int c = 1; c < K; ++c) {
+      const float v = p[c];
+      if (v > bv) {
+        bv = v;
+        best = c;
+      }
+    }
+    atomicAdd(counts + best, 1ull);
+  }
+}
+
+}  // namespace ap

@@ -1,0 +1,387 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle / golden fixtures.  Needs a B200.
+
+Tolerances (BASELINE.json north_star + SURVEY.md section 8c):
+  purified waveform rel-L2 <= 1e-2 (bf16 tensor-core mode); eps itself gated at 2e-2;
+  log-mel max-abs <= 2e-2 dB against torchaudio; vote counts bit-exact given the same noise.
+"""
+
+import ctypes
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import audiopure_b200 as ap
+from audiopure_b200 import _lib
+from oracle import certify as o_certify, purify as o_purify, resnext as o_resnext, schedule as o_schedule, \
+    wavenet as o_wavenet, weights as W
+from tests.emulate import emulate_eps
+
+pytestmark = pytest.mark.gpu
+
+EPS_GATE = 2e-2
+WAVE_GATE = 1e-2
+SMALL = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def make_model(cfg, seed):
+    m = ap.WaveNet_Speech_Commands(**cfg)
+    m.load_state_dict(W.make_state_dict(seed, cfg))
+    return m.cuda().eval()
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    return make_model(W.DEFAULT_WAVENET_CONFIG, 1234)
+
+
+@pytest.fixture(scope="module")
+def small_model():
+    return make_model(SMALL, 99)
+
+
+@pytest.fixture(scope="module")
+def hp():
+    return ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+
+
+@pytest.fixture(scope="module")
+def classifier():
+    clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
+    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    return clf.cuda().eval()
+
+
+# ----------------------------------------------------------------------------- bring-up: tcgen05 / TMA --
+@pytest.mark.parametrize("K", [64, 256, 768])
+def test_debug_gemm(K):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(K)
+    a = torch.randn(128, K, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(256, K, generator=g).to(torch.bfloat16).cuda()
+    d = torch.zeros(128, 256, device="cuda")
+    _lib.check(lib.ap_debug_gemm(a.data_ptr(), b.data_ptr(), d.data_ptr(), K, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    want = a.float().cpu() @ b.float().cpu().t()
+    assert rel_l2(d, want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ epsilon network --
+def test_eps_small_ragged_vs_emulation_oracle_golden(small_model, golden):
+    g = golden("wavenet_small.npz")
+    t = int(g["t"])
+    x = W.make_waveforms(3, 1000, seed=int(g["x_seed"]))
+    got = small_model((x.cuda(), t * torch.ones(3, 1))).cpu()
+    assert got.shape == (3, 1, 1000)
+    packed = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in small_model.engine().packed.items()}
+    emu = emulate_eps(packed, x, t, 6, 3, quantize=True)
+    assert rel_l2(got, emu) < 5e-3          # same rounding points: only accumulation order / tanh.approx differ
+    assert rel_l2(got, g["eps"]) < EPS_GATE  # reference output
+
+
+def test_layer_intermediates_vs_emulation(small_model):
+    """Every layer's gate tile (read back from the workspace) against the emulation: localises a bad layer,
+    including the clip edges and the ragged last tile (L = 1000 = 7*128 + 104)."""
+    x = W.make_waveforms(2, 1000, seed=11)
+    eng = small_model.engine()
+    eng.eps(x.cuda(), 3)
+    torch.cuda.synchronize()
+    B, L, layers = 2, 1000, 6
+    h_bytes = B * L * 256 * 2
+    ws = eng.workspace(B, L)
+    gate = ws[2 * h_bytes: 2 * h_bytes + layers * h_bytes].view(torch.bfloat16).view(layers, B, L, 256).float().cpu()
+    packed = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in eng.packed.items()}
+    _, inter = emulate_eps(packed, x, 3, 6, 3, quantize=True, return_inter=True)
+    for n in range(layers):
+        err = rel_l2(gate[n], inter["gate"][n])
+        assert err < 1e-2, "layer %d gate rel-L2 %.3e" % (n, err)
+        edge = torch.cat([gate[n][:, :8], gate[n][:, -8:]], 1)
+        want = torch.cat([inter["gate"][n][:, :8], inter["gate"][n][:, -8:]], 1)
+        assert rel_l2(edge, want) < 2e-2, "layer %d clip edges" % n
+
+
+@pytest.mark.parametrize("t", [1, 33])
+def test_eps_full_vs_golden(full_model, golden, t):
+    g = golden("wavenet_full.npz")
+    x = W.make_waveforms(1, 16000, seed=0)
+    got = full_model.engine().eps(x.cuda(), t)
+    assert rel_l2(got, g["eps_t%d" % t]) < EPS_GATE
+
+
+def test_eps_dilation_2048_layer_vs_golden(full_model, golden):
+    """Layers 0, 11 (dilation 2048) and 35 of the full network at the sampled time steps (clip edges included)."""
+    g = golden("wavenet_full.npz")
+    x = W.make_waveforms(1, 16000, seed=0)
+    eng = full_model.engine()
+    eng.eps(x.cuda(), 1)
+    torch.cuda.synchronize()
+    h_bytes = 16000 * 256 * 2
+    ws = eng.workspace(1, 16000)
+    idx = torch.from_numpy(g["slice_t"]).long()
+    sd = W.make_state_dict(1234)
+    for n in (0, 11, 35):
+        gate = ws[2 * h_bytes + n * h_bytes: 2 * h_bytes + (n + 1) * h_bytes].view(torch.bfloat16).view(16000, 256)
+        gate = gate.float().cpu()[idx]                                         # (64, 256)
+        ws_n = o_wavenet.fold_weight_norm(sd["residual_layer.residual_blocks.%d.skip_conv.weight_g" % n],
+                                          sd["residual_layer.residual_blocks.%d.skip_conv.weight_v" % n])[:, :, 0]
+        skip = gate @ ws_n.t() + sd["residual_layer.residual_blocks.%d.skip_conv.bias" % n]
+        want = torch.from_numpy(g["skip_%d" % n])[0].t()                        # (64, 256)
+        assert rel_l2(skip, want) < EPS_GATE, n
+
+
+def test_eps_is_batch_invariant_at_full_batch(full_model):
+    """BASELINE config 2 size (B = 64): every clip of the batch equals its own B = 1 evaluation bit for bit
+    (tiles never mix clips), so the small-case parity carries to the full size."""
+    x = W.make_waveforms(64, 16000, seed=2).cuda()
+    eng = full_model.engine()
+    big = eng.eps(x, 1)
+    for i in (0, 31, 63):
+        one = eng.eps(x[i:i + 1], 1)
+        assert torch.equal(big[i:i + 1], one), i
+    assert torch.isfinite(big).all()
+
+
+def test_eps_chunking_over_max_chunk():
+    m = ap.WaveNet_Speech_Commands(**SMALL, max_chunk=2)
+    m.load_state_dict(W.make_state_dict(99, SMALL))
+    m = m.cuda()
+    ref = make_model(SMALL, 99)
+    x = W.make_waveforms(5, 512, seed=4).cuda()
+    assert torch.equal(m.engine().eps(x, 2), ref.engine().eps(x, 2))
+
+
+# -------------------------------------------------------------------------------------------- purifiers --
+@pytest.mark.parametrize("t_star", [2, 3])
+def test_ddpm_purify_vs_reference(full_model, hp, golden, t_star):
+    g = golden("ddpm_t%d.npz" % t_star)
+    x = W.make_waveforms(2, 16000, seed=int(g["x_seed"]))
+    z = W.make_noise((t_star, 2, 1, 16000), seed=int(g["z_seed"]))
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=t_star)
+    y = dw(x.cuda(), z=z)
+    assert y.shape == x.shape and y.is_cuda
+    assert rel_l2(y, g["purified"]) < WAVE_GATE
+    # step-by-step surface (compute_coefficients / _diffusion / _reverse) agrees with the fused loop
+    y2 = dw._reverse(dw._diffusion(x.cuda(), z=z[0]), z=z[1:])
+    assert rel_l2(y2, y) < 1e-5
+
+
+def test_ddpm_accepts_numpy_and_leaves_input_intact(small_model, hp):
+    dw = ap.DiffWave(small_model, hp, reverse_timestep=2)
+    x = W.make_waveforms(2, 640, seed=1)
+    keep = x.clone()
+    xc = x.cuda()
+    y = dw(x.numpy())
+    assert y.shape == x.shape
+    dw(xc)
+    assert torch.equal(xc.cpu(), keep)
+
+
+def test_one_shot_vs_reference(full_model, hp, golden):
+    g = golden("oneshot_t34.npz")
+    x = W.make_waveforms(1, 16000, seed=0)
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=int(g["reverse_timestep"]))
+    assert rel_l2(dw.one_shot_denoise(x.cuda()), g["x0_hat"]) < WAVE_GATE
+
+
+def test_compute_coefficients_and_eps_t(full_model, hp, golden):
+    g = golden("wavenet_full.npz")
+    x = W.make_waveforms(1, 16000, seed=0).cuda()
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=2)
+    eps, mu, sigma = dw.compute_coefficients(x, 1)
+    assert rel_l2(eps, g["eps_t1"]) < EPS_GATE
+    a, ab = float(hp["Alpha"][1]), float(hp["Alpha_bar"][1])
+    want = (x.cpu() - (1 - a) / (1 - ab) ** 0.5 * torch.from_numpy(g["eps_t1"])) / a ** 0.5
+    assert rel_l2(mu, want) < 1e-3
+    assert float(sigma) == float(hp["Sigma"][1])
+    assert torch.equal(dw.compute_eps_t(x, torch.tensor(1)), eps)
+
+
+def test_sde_purify_vs_oracle(full_model, hp):
+    """torchsde is absent: the Euler-Maruyama restatement (oracle.purify.sde_purify, f/g pinned to the
+    reference's RevVPSDE) is the checker."""
+    sd = W.make_state_dict(1234)
+    tab = o_schedule.sde_tables()
+    t = 2
+    x = W.make_waveforms(1, 16000, seed=3)
+    z = W.make_noise((t + 1, 1, 1, 16000), seed=22)
+    want = o_purify.sde_purify(tab, lambda xx, k: o_wavenet.eps_theta(sd, xx, k), x, t, z[0], z[1:].reshape(t, 1, 16000))
+
+    class Args:
+        pass
+
+    args = Args()
+    args.t, args.sample_step, args.rand_t, args.t_delta, args.use_bm, args.score_type = t, 1, False, 0, False, "guided_diffusion"
+    rev = ap.RevDiffWave(args, model=ap.DiffWave(full_model, hp, reverse_timestep=t))
+    got = rev(x.cuda(), z=z[None])
+    assert got.shape == (1, 1, 16000)
+    assert rel_l2(got, want) < WAVE_GATE
+    # RevVPSDE.f / .g surface against the reference fixture
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "sde_fg.npz"))
+    xf = W.make_waveforms(1, 16000, seed=int(g["x_seed"])).view(1, -1).cuda()
+    for i, tc in enumerate(g["tc"]):
+        tt = torch.tensor(tc, dtype=torch.float32)
+        assert rel_l2(rev.rev_vpsde.f(tt, xf), g["f"][i]) < 2e-2
+        np.testing.assert_allclose(rev.rev_vpsde.g(tt, xf)[:, :4].cpu().numpy(), g["g"][i], rtol=1e-5, atol=0)
+
+
+def test_sde_sample_step_concatenates(small_model, hp):
+    class Args:
+        t, sample_step, rand_t, t_delta, use_bm, score_type = 2, 3, False, 0, False, "guided_diffusion"
+
+    rev = ap.RevDiffWave(Args(), model=ap.DiffWave(small_model, hp, reverse_timestep=2))
+    out = rev(W.make_waveforms(2, 512, seed=1).cuda())
+    assert out.shape == (6, 1, 512)  # diffwave_sde.py:212
+
+
+# ------------------------------------------------------------------------------------------ philox noise --
+def test_philox_noise_is_shard_invariant_and_seeded(small_model, hp):
+    dw = ap.DiffWave(small_model, hp, reverse_timestep=3, seed=5)
+    x = W.make_waveforms(4, 1024, seed=8).cuda()
+    eng = small_model.engine()
+    whole = eng.ddpm_purify(x, 3, seed=123)
+    again = eng.ddpm_purify(x, 3, seed=123)
+    assert torch.equal(whole, again)
+    halves = torch.cat([eng.ddpm_purify(x[:2], 3, seed=123, clip_offset=0),
+                        eng.ddpm_purify(x[2:], 3, seed=123, clip_offset=2)])
+    assert torch.equal(whole, halves)            # sharding the batch does not change the draws
+    other = eng.ddpm_purify(x, 3, seed=124)
+    assert not torch.equal(whole, other)
+    assert not torch.equal(dw(x), dw(x))         # successive forward() calls draw fresh noise
+
+
+def test_philox_normal_moments():
+    lib = _lib.load()
+    L, n = 4096, 256
+    x = torch.zeros(1, L, device="cuda")
+    out = torch.empty(n, 1, L, device="cuda")
+    _lib.check(lib.ap_smooth_inputs(x.data_ptr(), L, n, 1.0, 1.0, None, 42, 3, 0, out.data_ptr(), _lib.stream_ptr()))
+    v = out.double().flatten()
+    assert abs(float(v.mean())) < 5e-3 and abs(float(v.var()) - 1) < 1e-2
+    assert abs(float((v ** 4).mean()) - 3) < 0.05
+    # draws are keyed on the draw index: asking for draws [100, 110) reproduces that slice
+    sub = torch.empty(10, 1, L, device="cuda")
+    _lib.check(lib.ap_smooth_inputs(x.data_ptr(), L, 10, 1.0, 1.0, None, 42, 3, 100, sub.data_ptr(), _lib.stream_ptr()))
+    assert torch.equal(sub, out[100:110])
+
+
+# ------------------------------------------------------------------------------------------- front-end --
+def test_logmel_vs_torchaudio_fixture(golden):
+    g = golden("mel.npz")
+    x = torch.cat([W.make_waveforms(2, 16000, seed=0), torch.from_numpy(golden("ddpm_t2.npz")["purified"])], 0)
+    tr = ap.LogMelSpectrogram().cuda()
+    got = tr(x.cuda())
+    assert got.shape == (4, 1, 32, 32)
+    assert float((got.cpu() - torch.from_numpy(g["logmel"])).abs().max()) < 2e-2
+
+
+def test_logmel_ragged_lengths_and_silence():
+    from oracle import mel as o_mel
+
+    tr = ap.LogMelSpectrogram().cuda()
+    for L in (512, 8000, 16384 + 300):
+        x = W.make_waveforms(3, L, seed=L)
+        want = o_mel.log_mel(x)
+        got = tr(x.cuda())
+        assert got.shape == want.shape
+        assert float((got.cpu() - want).abs().max()) < 2e-2
+    z = tr(torch.zeros(1, 1, 16000, device="cuda"))
+    assert float(z.max()) == -100.0 and float(z.min()) == -100.0  # clamp at 1e-10 -> -100 dB
+
+
+# ------------------------------------------------------------------------- composition and certification --
+def test_acoustic_system_vs_reference(full_model, hp, classifier, golden):
+    g = golden("acoustic.npz")
+    x = W.make_waveforms(2, 16000, seed=0).cuda()
+    z = W.make_noise((2, 2, 1, 16000), seed=7)
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=2)
+
+    class Injected(torch.nn.Module):  # the defender slot is any callable (B,1,L)->(B,1,L)
+        def forward(self, w):
+            return dw(w, z=z)
+
+    AS = ap.AcousticSystem(classifier=classifier, transform=ap.LogMelSpectrogram().cuda(), defender=Injected())
+    with torch.no_grad():
+        logits = AS(x)
+        nodef = AS(x, defend=False)
+    assert rel_l2(nodef, g["logits_nodefend"]) < 1e-2
+    assert rel_l2(logits, g["logits"]) < 5e-2
+    assert np.array_equal(logits.argmax(1).cpu().numpy(), g["logits"].argmax(1))
+    with pytest.raises(NotImplementedError):
+        ap.AcousticSystem(classifier, None, dw, defense_type="other")
+
+
+def test_vote_counts_kernel_bit_exact():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(1000, 10, generator=g)
+    logits[::7, 3] = logits[::7, 5] = 9.0  # ties: lowest index wins, like torch.max
+    counts = torch.zeros(10, dtype=torch.int64, device="cuda")
+    lc = logits.cuda()
+    _lib.check(lib.ap_vote_counts(lc.data_ptr(), 1000, 10, counts.data_ptr(), _lib.stream_ptr()))
+    assert torch.equal(counts.cpu(), o_certify.vote_counts(logits, 10))
+    assert int(counts.sum()) == 1000
+
+
+def test_smooth_predict_counts_vs_reference(full_model, hp, classifier, golden):
+    g = golden("smooth.npz")
+    x = W.make_waveforms(1, 16000, seed=0)[0].cuda()
+    z = W.make_noise((6, 1, 16000), seed=int(g["z_seed"]))
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=2)
+    RC = ap.RobustCertificate(classifier=classifier, transform=ap.LogMelSpectrogram().cuda(), denoiser=dw)
+    counts = RC.smooth_predict(x, num_sampling=6, sigma=float(g["sigma"]), batch_size=int(g["batch_size"]), z=z)
+    assert dw.reverse_timestep == int(g["t_star"])  # the certifier retargets the denoiser (certified_robust.py:53)
+    assert counts.dtype == torch.int64 and not counts.is_cuda
+    assert np.array_equal(counts.numpy(), g["counts"])
+
+
+def test_certify_end_to_end_and_abstain(small_model, hp, classifier):
+    dw = ap.DiffWave(small_model, hp, reverse_timestep=2)
+    RC = ap.RobustCertificate(classifier=classifier, transform=ap.LogMelSpectrogram().cuda(), denoiser=dw, seed=1)
+    x = W.make_waveforms(2, 16000, seed=9).cuda()
+    y = torch.zeros(2, dtype=torch.long, device="cuda")
+    y_pred, radius = RC.certify(x, y, sigma=0.25, n_0=8, n=32, batch_size=16)
+    assert y_pred.shape == (2,) and radius.shape == (2,)
+    for c, r in zip(y_pred.tolist(), radius.tolist()):
+        assert (c == -1 and r == 0.0) or (0 <= c < 10 and r > 0)
+    # same seed -> same draws -> same certificate
+    y2, r2 = ap.RobustCertificate(classifier, ap.LogMelSpectrogram().cuda(), dw, seed=1).certify(
+        x, y, sigma=0.25, n_0=8, n=32, batch_size=16)
+    assert torch.equal(y_pred, y2) and torch.equal(radius, r2)
+
+
+def test_sharded_counts_equal_single_rank(small_model, hp, classifier):
+    """Two logical ranks on one GPU: disjoint draw slices, summed counts == the unsharded counts."""
+    dw = ap.DiffWave(small_model, hp, reverse_timestep=2)
+    tr = ap.LogMelSpectrogram().cuda()
+    x = W.make_waveforms(1, 16000, seed=4)[0].cuda()
+    whole = ap.RobustCertificate(classifier, tr, dw, seed=3).smooth_predict(x, 37, 0.25, batch_size=37)
+    parts = []
+    for r in range(2):
+        rc = ap.RobustCertificate(classifier, tr, dw, seed=3, rank=r, world_size=2, allreduce=lambda c: c)
+        lo, hi = ap.certified_robust.shard_range(37, r, 2)
+        parts.append(rc.smooth_predict(x, 37, 0.25, batch_size=hi - lo))
+    assert int(whole.sum()) == 37
+    assert torch.equal(parts[0] + parts[1], whole)
+
+
+# ---------------------------------------------------------------------------------------- error behaviour --
+def test_errors_are_loud(small_model, hp):
+    lib = _lib.load()
+    eng = small_model.engine()
+    with pytest.raises(_lib.AudioPureError):
+        eng.eps(torch.zeros(1, 1, 512, device="cuda"), 200)          # t out of range
+    with pytest.raises(_lib.AudioPureError):
+        eng.ddpm_purify(torch.zeros(1, 1, 512, device="cuda"), 0)    # t* out of range
+    with pytest.raises(_lib.AudioPureError):
+        _lib.check(lib.ap_eps(eng.handle, None, 1, 512, 0, None, None, 0, None))
+    with pytest.raises(_lib.AudioPureError):
+        ap.LogMelSpectrogram()(torch.zeros(1, 1, 16000))             # CPU tensor: no fallback
+    with pytest.raises(AssertionError):
+        ap.DiffWave(small_model, hp)(torch.zeros(4, 16000, device="cuda"))  # ndim == 3 (diffwave_ddpm.py:62)

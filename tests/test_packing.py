@@ -1,0 +1,77 @@
+"""Host logic on the CPU: state-dict layout, weight packing and the kernel dataflow (emulated in torch)
+against the oracle.  No GPU, no compute through the C ABI."""
+
+import json
+
+import pytest
+import torch
+
+import audiopure_b200 as ap
+from oracle import schedule as o_schedule, wavenet as o_wavenet, weights as W
+from tests.emulate import emulate_eps
+
+SMALL = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def test_state_dict_layout_matches_reference():
+    m = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
+    sd = W.make_state_dict(1234)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert all(m.state_dict()[k].shape == v.shape for k, v in sd.items())
+    m.load_state_dict(sd)  # strict
+    # default init leaves the output conv at zero, like ZeroConv1d (WaveNet.py:39-44)
+    fresh = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
+    assert float(fresh.state_dict()["final_conv.2.conv.weight"].abs().max()) == 0.0
+
+
+def test_unsupported_widths_are_rejected():
+    with pytest.raises(NotImplementedError):
+        ap.WaveNet_Speech_Commands(res_channels=128, skip_channels=128)
+
+
+def test_schedule_matches_oracle_bit_exact():
+    a = ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    b = o_schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    for k in ("Beta", "Alpha", "Alpha_bar", "Sigma"):
+        assert torch.equal(a[k], b[k])
+    steps = torch.tensor([[0.0], [5.0], [199.0]])
+    assert torch.equal(ap.calc_diffusion_step_embedding(steps, 128), o_schedule.calc_diffusion_step_embedding(steps, 128))
+
+
+@pytest.mark.parametrize("t", [0, 7, 199])
+def test_packed_dataflow_fp32_equals_oracle(t):
+    """With no bf16 rounding the packed reformulation (permuted rows, tap-major K, folded sqrt(.5) and
+    sqrt(1/N), shift folded into the previous layer's epilogue, deferred skip GEMM) IS the reference network."""
+    sd = W.make_state_dict(99, SMALL)
+    m = ap.WaveNet_Speech_Commands(**SMALL)
+    m.load_state_dict(sd)
+    packed = {k: (v.float() if torch.is_tensor(v) else v) for k, v in m.pack_weights("cpu").items()}
+    # undo the bf16 cast of the GEMM operands by re-packing in fp32
+    x = W.make_waveforms(2, 1000, seed=5)
+    want = o_wavenet.eps_theta(sd, x, t, SMALL)
+    got = emulate_eps(packed, x, t, 6, 3, quantize=False)
+    # operands were rounded to bf16 at pack time: ~2^-9 relative per weight
+    assert rel_l2(got, want) < 6e-3
+
+
+def test_packed_dataflow_bf16_within_gate():
+    """The bf16 rounding points of the kernels keep eps inside the 2e-2 gate (SURVEY section 7 numerics)."""
+    sd = W.make_state_dict(99, SMALL)
+    m = ap.WaveNet_Speech_Commands(**SMALL)
+    m.load_state_dict(sd)
+    packed = m.pack_weights("cpu")
+    x = W.make_waveforms(2, 1000, seed=5)
+    want = o_wavenet.eps_theta(sd, x, 7, SMALL)
+    got = emulate_eps(packed, x, 7, 6, 3, quantize=True)
+    assert rel_l2(got, want) < 2e-2
+
+
+def test_packing_is_refreshed_after_load_state_dict():
+    m = ap.WaveNet_Speech_Commands(**SMALL)
+    m._engine = object()
+    m.load_state_dict(W.make_state_dict(99, SMALL))
+    assert m._engine is None

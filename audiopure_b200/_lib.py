@@ -13,7 +13,8 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 c_i32_p = ctypes.POINTER(ctypes.c_int32)
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 
-AP_ABI_VERSION = 1
+AP_ABI_VERSION = 2
+AP_FLAG_SINGLE_CTA = 1
 AP_COMM_ID_BYTES = 128
 
 
@@ -23,6 +24,7 @@ class ApConfig(ctypes.Structure):
         ("dilation_cycle", ctypes.c_int32),
         ("T", ctypes.c_int32),
         ("max_chunk", ctypes.c_int32),
+        ("flags", ctypes.c_uint32),
         ("alpha", c_float_p),
         ("alpha_bar", c_float_p),
         ("sigma", c_float_p),

@@ -82,6 +82,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct ap_net {
   int layers = 0, cycle = 0, T = 0, max_chunk = 64;
+  bool pair = true;  // CTA-pair (cta_group::2) kernels
   ap_weights w{};
   std::vector<float> alpha, alpha_bar, sigma, sde_beta, sde_acp;
   CUtensorMap tm_w1, tm_w2, tm_ws, tm_wf;
@@ -193,7 +194,25 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   }
   const int tiles_per_clip = (L + ap::kTileT - 1) / ap::kTileT;
   const int num_tiles = tiles_per_clip * Bc;
-  const int grid = num_tiles < n->num_sms ? num_tiles : n->num_sms;
+  // persistent grid: one CTA per SM, or one CTA pair (cluster of 2) per TPC
+  int grid;
+  if (n->pair) {
+    const int units = (num_tiles + 1) / 2, clusters = n->num_sms / 2;
+    grid = 2 * (units < clusters ? units : clusters);
+  } else {
+    grid = num_tiles < n->num_sms ? num_tiles : n->num_sms;
+  }
+  cudaLaunchConfig_t lc{};
+  cudaLaunchAttribute cluster_attr{};
+  cluster_attr.id = cudaLaunchAttributeClusterDimension;
+  cluster_attr.val.clusterDim.x = 2;
+  cluster_attr.val.clusterDim.y = 1;
+  cluster_attr.val.clusterDim.z = 1;
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(ap::kThreads);
+  lc.stream = st;
+  lc.attrs = &cluster_attr;
+  lc.numAttrs = 1;
   for (int l = 0; l < n->layers; ++l) {
     ap::LayerArgs a;
     a.b1 = n->w.b1 + static_cast<size_t>(l) * 512;
@@ -208,7 +227,13 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
     a.layer = l;
     a.write_h = (l + 1 < n->layers) ? 1 : 0;
     ProfSpan span(n, st, 0);
-    ap::layer_kernel<<<grid, ap::kThreads, ap::kLayerSmem, st>>>(n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate, a);
+    if (n->pair) {
+      lc.dynamicSmemBytes = ap::Tc<true>::kLayerSmem;
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<true>, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate, a));
+    } else {
+      ap::layer_kernel<false><<<grid, ap::kThreads, ap::Tc<false>::kLayerSmem, st>>>(n->tm_h[l & 1], n->tm_w1, n->tm_w2,
+                                                                                     n->tm_gate, a);
+    }
   }
   tail.bs = n->w.bs;
   tail.bf = n->w.bf;
@@ -221,7 +246,12 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   tail.num_layers = n->layers;
   {
     ProfSpan span(n, st, 1);
-    ap::tail_kernel<<<grid, ap::kThreads, ap::kTailSmem, st>>>(n->tm_gate, n->tm_ws, n->tm_wf, tail);
+    if (n->pair) {
+      lc.dynamicSmemBytes = ap::Tc<true>::kTailSmem;
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<true>, n->tm_gate, n->tm_ws, n->tm_wf, tail));
+    } else {
+      ap::tail_kernel<false><<<grid, ap::kThreads, ap::Tc<false>::kTailSmem, st>>>(n->tm_gate, n->tm_ws, n->tm_wf, tail);
+    }
   }
   AP_CUDA(cudaGetLastError());
   return 0;
@@ -321,6 +351,7 @@ int ap_create(const ap_config* cfg, const ap_weights* w, ap_net** out) {
   n->cycle = cfg->dilation_cycle;
   n->T = cfg->T;
   n->max_chunk = cfg->max_chunk > 0 ? cfg->max_chunk : 64;
+  n->pair = (cfg->flags & AP_FLAG_SINGLE_CTA) == 0;
   n->w = *w;
   n->alpha.assign(cfg->alpha, cfg->alpha + cfg->T);
   n->alpha_bar.assign(cfg->alpha_bar, cfg->alpha_bar + cfg->T);
@@ -331,19 +362,23 @@ int ap_create(const ap_config* cfg, const ap_weights* w, ap_net** out) {
   n->device = dev;
   const uint64_t L = static_cast<uint64_t>(n->layers);
   const uint64_t dw1[2] = {768, L * 512}, dw2[2] = {256, L * 256}, dws[2] = {L * 256, 256}, dwf[2] = {256, 256};
-  int rc = make_map(&n->tm_w1, w->w1, 2, dw1, 256) || make_map(&n->tm_w2, w->w2, 2, dw2, 256) ||
-           make_map(&n->tm_ws, w->ws, 2, dws, 256) || make_map(&n->tm_wf, w->wf, 2, dwf, 256);
+  const uint32_t brows = n->pair ? 128 : 256;  // weight rows staged per CTA per K step
+  int rc = make_map(&n->tm_w1, w->w1, 2, dw1, brows) || make_map(&n->tm_w2, w->w2, 2, dw2, brows) ||
+           make_map(&n->tm_ws, w->ws, 2, dws, brows) || make_map(&n->tm_wf, w->wf, 2, dwf, brows);
   if (rc) {
     delete n;
     return 1;
   }
-  cudaError_t e1 = cudaFuncSetAttribute(ap::layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::kLayerSmem);
-  cudaError_t e2 = cudaFuncSetAttribute(ap::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::kTailSmem);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    delete n;
-    return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") +
-                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-  }
+  cudaError_t es[4] = {
+      cudaFuncSetAttribute(ap::layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<false>::kLayerSmem),
+      cudaFuncSetAttribute(ap::tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<false>::kTailSmem),
+      cudaFuncSetAttribute(ap::layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<true>::kLayerSmem),
+      cudaFuncSetAttribute(ap::tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<true>::kTailSmem)};
+  for (cudaError_t e : es)
+    if (e != cudaSuccess) {
+      delete n;
+      return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e));
+    }
   *out = n;
   return 0;
 }
@@ -514,7 +549,7 @@ int ap_debug_gemm(const void* a_bf16, const void* b_bf16, float* d, int K, void*
   CUtensorMap ta, tb;
   const uint64_t da[2] = {static_cast<uint64_t>(K), 128}, db[2] = {static_cast<uint64_t>(K), 256};
   if (make_map(&ta, a_bf16, 2, da, 128) || make_map(&tb, b_bf16, 2, db, 256)) return 1;
-  const int smem = ap::kStageBytes + 64 + 1024;
+  const int smem = ap::kABytes + 256 * 128 + 64 + 1024;
   AP_CUDA(cudaFuncSetAttribute(ap::debug_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   ap::debug_gemm_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, d, K);
   AP_CUDA(cudaGetLastError());

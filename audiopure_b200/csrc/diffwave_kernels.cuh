@@ -19,10 +19,7 @@ namespace ap {
 
 constexpr int kC = 256;          // residual / skip / gate channels (the only width the kernels support)
 constexpr int kTileT = 128;      // time steps per tile = UMMA M
-constexpr int kStages = 3;       // TMA -> MMA ring depth
-constexpr uint32_t kABytes = kTileT * 128;  // [128 rows x 64 bf16]
-constexpr uint32_t kBBytes = 256 * 128;     // [256 rows x 64 bf16]
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kABytes = kTileT * 128;  // [128 rows x 64 bf16]: one K step of activations
 constexpr uint32_t kTileBytes = kTileT * kC * 2;  // a full [128 x 256] bf16 operand tile (4 swizzled sub-tiles)
 constexpr int kThreads = 384;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-3: idle, warps 4-11: epilogue
 constexpr int kEpiWarp0 = 4;
@@ -30,8 +27,6 @@ constexpr int kEpiThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr float kSqrtHalf = 0.70710678118654752440f;
 
-constexpr uint32_t kLayerSmem = kStages * kStageBytes + kTileBytes + 512 * 4 + 256 * 4 + 16 * 8 + 16 + 1024;
-constexpr uint32_t kTailSmem = kStages * kStageBytes + kTileBytes + 3 * 256 * 4 + 2 * 2 * 128 * 4 + 16 * 8 + 16 + 1024;
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -107,6 +102,118 @@ __global__ void __launch_bounds__(256) prologue_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Shared plumbing of the two tensor-core kernels.  kPair = false: one CTA per 128-step tile, tcgen05
+// cta_group::1 (M = 128).  kPair = true: a cluster of two CTAs (the two SMs of a TPC) per pair of tiles,
+// cta_group::2 (M = 256): each CTA stages its own 128 activation rows and HALF of the weight rows, the
+// leader CTA issues the MMAs for both, each CTA's TMEM receives its own tile's accumulators and each CTA runs
+// its own epilogue.  Per SM this halves the weight bytes written into shared memory and the weight bytes the
+// tensor core reads back out of it -- shared-memory bandwidth, not the tensor pipe, is what caps the 1-CTA form.
+// ---------------------------------------------------------------------------------------------------
+template <bool kPair>
+struct Tc {
+  static constexpr int kStages = kPair ? 4 : 3;              // TMA -> MMA ring depth
+  static constexpr uint32_t kBRows = kPair ? 128 : 256;      // weight rows staged per CTA per K step
+  static constexpr uint32_t kBBytes = kBRows * 128;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kRing = kStages * kStageBytes;
+  static constexpr uint32_t kCtas = kPair ? 2 : 1;
+  static constexpr uint32_t kEpiArrivals = kCtas * (kEpiThreads / 32);  // epilogue -> MMA barrier arrival count
+  static constexpr uint32_t kIdesc = umma_idesc_bf16(kPair ? 256 : 128, 256);
+  static constexpr uint32_t kLayerSmem = kRing + kTileBytes + 512 * 4 + 256 * 4 + 32 * 8 + 1024;
+  static constexpr uint32_t kTailSmem = kRing + kTileBytes + 3 * 256 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 1024;
+
+  // Barrier the LEADER's MMA thread waits on: returns the address every CTA of the pair should arrive at.
+  static __device__ __forceinline__ uint32_t leader_addr(uint64_t* bar) {
+    if constexpr (kPair) return mapa_u32(bar, 0);
+    else return smem_u32(bar);
+  }
+  static __device__ __forceinline__ void arrive_leader(uint32_t addr) {
+    if constexpr (kPair) mbar_arrive_cluster(addr);
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+  }
+  static __device__ __forceinline__ void expect_leader(uint32_t addr, uint32_t bytes) {
+    if constexpr (kPair) mbar_arrive_expect_tx_cluster(addr, bytes);
+    else asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+  }
+  static __device__ __forceinline__ void wait_leader(uint64_t* bar, uint32_t parity, int tag) {
+    mbar_wait(bar, parity, tag);
+  }
+  static __device__ __forceinline__ void load2(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    if constexpr (kPair) tma_load_2d_pair(dst, m, bar, c0, c1);
+    else
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+              "r"(smem_u32(dst)),
+          "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+          : "memory");
+  }
+  static __device__ __forceinline__ void load3(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+    if constexpr (kPair) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
+    else
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+          "[%2];" ::"r"(smem_u32(dst)),
+          "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+          : "memory");
+  }
+  static __device__ __forceinline__ void load4(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                               int c3) {
+    if constexpr (kPair) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+    else
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+          "[%2];" ::"r"(smem_u32(dst)),
+          "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+          : "memory");
+  }
+  static __device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+    if constexpr (kPair) umma_bf16_pair(d, da, db, kIdesc, acc);
+    else umma_bf16(d, da, db, kIdesc, acc);
+  }
+  static __device__ __forceinline__ void commit(uint64_t* bar) {
+    if constexpr (kPair) umma_commit_pair(bar);
+    else umma_commit(bar);
+  }
+  static __device__ __forceinline__ void block_sync() {  // every thread of the CTA (pair: of both CTAs)
+    if constexpr (kPair) cluster_sync_all();
+    else __syncthreads();
+  }
+  static __device__ __forceinline__ void tmem_allocate(uint32_t* dst) {
+    if constexpr (kPair) {
+      tmem_alloc_pair(dst, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(dst, kTmemCols);
+      tmem_relinquish();
+    }
+  }
+  static __device__ __forceinline__ void tmem_free(uint32_t addr) {
+    if constexpr (kPair) tmem_dealloc_pair(addr, kTmemCols);
+    else tmem_dealloc(addr, kTmemCols);
+  }
+};
+
+// Work distribution shared by all warp roles: unit u covers tiles [u*kCtas, u*kCtas + kCtas); this CTA takes
+// tile u*kCtas + rank.  A pair whose second tile does not exist gives that CTA an all-out-of-bounds tile
+// (TMA zero-fills its loads, its stores are masked) so that both CTAs walk identical barrier sequences.
+struct TileCoord {
+  int b, l0;
+  bool valid;
+};
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_tiles, int tiles_per_clip) {
+  TileCoord t;
+  t.valid = tile < num_tiles;
+  if (t.valid) {
+    t.b = tile / tiles_per_clip;
+    t.l0 = (tile - t.b * tiles_per_clip) * kTileT;
+  } else {
+    t.b = 0;
+    t.l0 = tiles_per_clip * kTileT;
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K1: one residual layer (WaveNet.py:75-97), fully fused, persistent over 128-step tiles.
 //
 //   GEMM1  D1[128 x 512] = sum_{tap,c} h[l + (tap-1)d][c] * W1[o][c][tap]     (K = 768)
@@ -132,124 +239,137 @@ struct LayerArgs {
   int write_h;                 // 0 for the last layer (its residual output is never consumed)
 };
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w1,
              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_gate,
              const LayerArgs a) {
+  using T = Tc<kPair>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
-  uint8_t* gate_s = smem + kStages * kStageBytes;
+  uint8_t* gate_s = smem + T::kRing;
   float* b1s = reinterpret_cast<float*>(gate_s + kTileBytes);
   float* c2s = b1s + 512;
   uint64_t* bars = reinterpret_cast<uint64_t*>(c2s + 256);
-  uint64_t* full = bars;            // [kStages] TMA -> MMA
-  uint64_t* empty = bars + 3;       // [kStages] MMA -> TMA
-  uint64_t* d1_full = bars + 6;     // [2] chunk accumulator ready        MMA -> epilogue
-  uint64_t* gate_ready = bars + 8;  // [2] gate half in smem, chunk's TMEM drained   epilogue -> MMA
-  uint64_t* d2_full = bars + 10;    //     residual accumulator ready     MMA -> epilogue
-  uint64_t* d2_empty = bars + 11;   //     residual accumulator drained   epilogue -> MMA
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* full = bars;             // [kStages] TMA -> MMA            (leader's copy is the live one)
+  uint64_t* empty = bars + 4;        // [kStages] MMA -> TMA            (per CTA, multicast commit)
+  uint64_t* d1_full = bars + 8;      // [2] chunk accumulator ready     MMA -> epilogue (per CTA)
+  uint64_t* gate_ready = bars + 10;  // [2] gate half in smem, chunk's TMEM drained   epilogue -> MMA (leader)
+  uint64_t* d2_full = bars + 12;     //     residual accumulator ready  MMA -> epilogue (per CTA)
+  uint64_t* d2_empty = bars + 13;    //     residual accumulator drained epilogue -> MMA (leader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int units = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+
   for (int i = threadIdx.x; i < 512; i += kThreads) b1s[i] = a.b1[i];
   for (int i = threadIdx.x; i < 256; i += kThreads) c2s[i] = a.c2[i];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 1);
+    for (int s = 0; s < T::kStages; ++s) {
+      mbar_init(&full[s], T::kCtas);
       mbar_init(&empty[s], 1);
     }
     mbar_init(&d1_full[0], 1);
     mbar_init(&d1_full[1], 1);
-    mbar_init(&gate_ready[0], kEpiThreads / 32);
-    mbar_init(&gate_ready[1], kEpiThreads / 32);
+    mbar_init(&gate_ready[0], T::kEpiArrivals);
+    mbar_init(&gate_ready[1], T::kEpiArrivals);
     mbar_init(d2_full, 1);
-    mbar_init(d2_empty, kEpiThreads / 32);
+    mbar_init(d2_empty, T::kEpiArrivals);
     fence_mbar_init();
     tma_prefetch_desc(&tm_h);
     tma_prefetch_desc(&tm_w1);
     tma_prefetch_desc(&tm_w2);
     tma_prefetch_desc(&tm_gate);
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr, kTmemCols);
-    tmem_relinquish();
-  }
+  if (warp == 1) T::tmem_allocate(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  T::block_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_clip;
-        const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
-        for (int c = 0; c < 2; ++c) {
-          for (int ks = 0; ks < 12; ++ks, ++it) {
-            const int s = it % kStages;
-            mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 1);
-            mbar_arrive_expect_tx(&full[s], kStageBytes);
-            uint8_t* sa = stage_base + s * kStageBytes;
+    // ======================= TMA producer (whole warp walks the loop; one elected lane issues) ==========
+    const uint32_t full0 = T::leader_addr(&full[0]);
+    const int brow = static_cast<int>(rank * T::kBRows);
+    uint32_t it = 0;
+    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units) {
+      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+      for (int c = 0; c < 2; ++c) {
+        for (int ks = 0; ks < 12; ++ks, ++it) {
+          const int s = it % T::kStages;
+          mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 1);
+          if (elect_one()) {
+            T::expect_leader(full0 + 8 * s, T::kStageBytes);
+            uint8_t* sa = stage_base + s * T::kStageBytes;
             const int tap = ks >> 2;
-            tma_load_3d(sa, &tm_h, &full[s], (ks & 3) * 64, l0 + (tap - 1) * a.dilation, b);
-            tma_load_2d(sa + kABytes, &tm_w1, &full[s], ks * 64, a.layer * 512 + c * 256);
+            T::load3(sa, &tm_h, full0 + 8 * s, (ks & 3) * 64, tc.l0 + (tap - 1) * a.dilation, tc.b);
+            T::load2(sa + kABytes, &tm_w1, full0 + 8 * s, ks * 64, a.layer * 512 + c * 256 + brow);
           }
+          __syncwarp();
         }
-        for (int ks = 0; ks < 4; ++ks, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 2);
-          mbar_arrive_expect_tx(&full[s], kBBytes);
-          tma_load_2d(stage_base + s * kStageBytes + kABytes, &tm_w2, &full[s], ks * 64, a.layer * 256);
+      }
+      for (int ks = 0; ks < 4; ++ks, ++it) {
+        const int s = it % T::kStages;
+        mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 2);
+        if (elect_one()) {
+          T::expect_leader(full0 + 8 * s, T::kBBytes);
+          T::load2(stage_base + s * T::kStageBytes + kABytes, &tm_w2, full0 + 8 * s, ks * 64, a.layer * 256 + brow);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    // ======================= MMA issuer (leader CTA; whole warp walks the loop, one lane issues) ========
+    if (rank == 0) {
+      const uint64_t desc0 = umma_desc_sw128(smem_u32(stage_base));  // descriptors differ only in the address field
+      const uint64_t gdesc0 = umma_desc_sw128(smem_u32(gate_s));
       uint32_t it = 0;
       int i = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
+      for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
         const uint32_t p = i & 1;
         const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
         for (int c = 0; c < 2; ++c) {
           if (c == 1 && i > 0) {  // bufB held the previous tile's residual accumulator
-            mbar_wait(d2_empty, (i - 1) & 1, 3);
+            T::wait_leader(d2_empty, (i - 1) & 1, 3);
             tc_fence_after();
           }
           const uint32_t d = c ? bufB : bufA;
           for (int ks = 0; ks < 12; ++ks, ++it) {
-            const int s = it % kStages;
-            mbar_wait(&full[s], (it / kStages) & 1, 4);
+            const int s = it % T::kStages;
+            T::wait_leader(&full[s], (it / T::kStages) & 1, 4);
             tc_fence_after();
-            const uint32_t sa = smem_u32(stage_base + s * kStageBytes);
-            const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
+            if (elect_one()) {
+              const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
+              const uint64_t db = da + static_cast<uint64_t>(kABytes >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
-            umma_commit(&empty[s]);
+              for (int k = 0; k < 4; ++k) T::mma(d, da + 2 * k, db + 2 * k, (ks | k) != 0);
+              T::commit(&empty[s]);
+              if (ks == 11) T::commit(&d1_full[c]);
+            }
+            __syncwarp();
           }
-          umma_commit(&d1_full[c]);
         }
         for (int ks = 0; ks < 4; ++ks, ++it) {
           if (ks == 0 || ks == 2) {  // K 0..127 needs gate half 0 (and bufA drained), K 128..255 half 1
-            mbar_wait(&gate_ready[ks >> 1], p, 5);
+            T::wait_leader(&gate_ready[ks >> 1], p, 5);
             tc_fence_after();
           }
-          const int s = it % kStages;
-          mbar_wait(&full[s], (it / kStages) & 1, 6);
+          const int s = it % T::kStages;
+          T::wait_leader(&full[s], (it / T::kStages) & 1, 6);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(gate_s + ks * kABytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(stage_base + s * kStageBytes + kABytes));
+          if (elect_one()) {
+            const uint64_t da = gdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
+            const uint64_t db = desc0 + static_cast<uint64_t>((s * T::kStageBytes + kABytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(bufA, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
-          umma_commit(&empty[s]);
+            for (int k = 0; k < 4; ++k) T::mma(bufA, da + 2 * k, db + 2 * k, (ks | k) != 0);
+            T::commit(&empty[s]);
+            if (ks == 3) T::commit(d2_full);
+          }
+          __syncwarp();
         }
-        umma_commit(d2_full);
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -259,11 +379,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     const int hh = e >> 2;    // which half of the columns this warpgroup handles
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t gate_ready0 = T::leader_addr(&gate_ready[0]);
+    const uint32_t d2_empty_l = T::leader_addr(d2_empty);
     int i = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
+    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
       const uint32_t p = i & 1;
-      const int b = tile / a.tiles_per_clip;
-      const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
+      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+      const int b = tc.b, l0 = tc.l0;
       const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
       const bool row_ok = (l0 + row) < a.L;
 
@@ -301,31 +423,34 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&gate_ready[c]);
+        if (lane == 0) T::arrive_leader(gate_ready0 + 8 * c);
       }
 
       // ---- gate tile -> HBM (operand of the tail's skip GEMM) ----
       named_bar_sync(1, kEpiThreads);
-      if (e == 0 && lane == 0) {
+      if (e == 0 && lane == 0 && tc.valid) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) tma_store_4d(&tm_gate, gate_s + s * kABytes, s * 64, l0, b, a.layer);
         tma_store_commit();
       }
 
-      // ---- residual output ----
+      // ---- residual output (x is prefetched one 32-channel group ahead to hide the load latency) ----
+      const size_t grow = (static_cast<size_t>(b) * a.L + l0 + row) * kC;
+      const uint4* xsrc = reinterpret_cast<const uint4*>(a.h_in + grow + hh * 128);
+      uint4 xn[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) xn[v] = row_ok ? __ldg(xsrc + v) : make_uint4(0, 0, 0, 0);
       mbar_wait(d2_full, p, 8);
       tc_fence_after();
-      const size_t grow = (static_cast<size_t>(b) * a.L + l0 + row) * kC;
-#pragma unroll 1
+#pragma unroll
       for (int itn = 0; itn < 4; ++itn) {
         const int j0 = hh * 128 + itn * 32;
         uint4 xv[4];
-        if (row_ok) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) xv[v] = __ldg(reinterpret_cast<const uint4*>(a.h_in + grow + j0) + v);
-        } else {
+        for (int v = 0; v < 4; ++v) xv[v] = xn[v];
+        if (itn < 3) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) xv[v] = make_uint4(0, 0, 0, 0);
+          for (int v = 0; v < 4; ++v) xn[v] = row_ok ? __ldg(xsrc + (itn + 1) * 4 + v) : make_uint4(0, 0, 0, 0);
         }
         uint32_t r[32];
         tmem_ld32(bufA + lane_addr + j0, r);
@@ -346,7 +471,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(d2_empty);
+      if (lane == 0) T::arrive_leader(d2_empty_l);
       // the gate tile in smem is rewritten by the next tile: its TMA store must have finished reading it
       if (e == 0 && lane == 0) tma_store_wait_read();
       named_bar_sync(1, kEpiThreads);
@@ -355,10 +480,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   }
 
   tc_fence_before();
-  __syncthreads();
+  T::block_sync();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    T::tmem_free(tmem_base);
   }
 }
 
@@ -391,54 +516,57 @@ struct TailArgs {
   int B, L, tiles_per_clip, num_tiles, num_layers;
 };
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__ CUtensorMap tm_ws,
             const __grid_constant__ CUtensorMap tm_wf, const TailArgs a) {
+  using T = Tc<kPair>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
-  uint8_t* s_tile = smem + kStages * kStageBytes;
+  uint8_t* s_tile = smem + T::kRing;
   float* bss = reinterpret_cast<float*>(s_tile + kTileBytes);
   float* bfs = bss + 256;
   float* wos = bfs + 256;
   float* partial = wos + 256;  // [2 parities][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(partial + 512);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 3;
-  uint64_t* d_full = bars + 6;    // [2] skip accumulator ready      MMA -> epilogue
-  uint64_t* d_empty = bars + 8;   // [2] buffer fully consumed       epilogue -> MMA
-  uint64_t* s_ready = bars + 10;  //     bf16 skip tile in smem      epilogue -> MMA
-  uint64_t* d3_full = bars + 11;  // [2] head accumulator ready      MMA -> epilogue
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* full = bars;           // [kStages]                        (leader)
+  uint64_t* empty = bars + 4;      // [kStages]                        (per CTA)
+  uint64_t* d_full = bars + 8;     // [2] skip accumulator ready       MMA -> epilogue (per CTA)
+  uint64_t* d_empty = bars + 10;   // [2] buffer fully consumed        epilogue -> MMA (leader)
+  uint64_t* s_ready = bars + 12;   //     bf16 skip tile in smem       epilogue -> MMA (leader)
+  uint64_t* d3_full = bars + 13;   // [2] head accumulator ready       MMA -> epilogue (per CTA)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int units = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+
   for (int i = threadIdx.x; i < 256; i += kThreads) {
     bss[i] = a.bs[i];
     bfs[i] = a.bf[i];
     wos[i] = a.wo[i];
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 1);
+    for (int s = 0; s < T::kStages; ++s) {
+      mbar_init(&full[s], T::kCtas);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&d_full[s], 1);
-      mbar_init(&d_empty[s], kEpiThreads / 32);
+      mbar_init(&d_empty[s], T::kEpiArrivals);
       mbar_init(&d3_full[s], 1);
     }
-    mbar_init(s_ready, kEpiThreads / 32);
+    mbar_init(s_ready, T::kEpiArrivals);
     fence_mbar_init();
     tma_prefetch_desc(&tm_gate);
     tma_prefetch_desc(&tm_ws);
     tma_prefetch_desc(&tm_wf);
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr, kTmemCols);
-    tmem_relinquish();
-  }
+  if (warp == 1) T::tmem_allocate(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  T::block_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -446,74 +574,84 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   const int J = total_ks / 2 < 16 ? total_ks / 2 : 16;  // where the previous tile's head GEMM is slotted in
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      int i = 0;
-      auto load_wf = [&]() {
-        for (int ks = 0; ks < 4; ++ks, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 11);
-          mbar_arrive_expect_tx(&full[s], kBBytes);
-          tma_load_2d(stage_base + s * kStageBytes + kABytes, &tm_wf, &full[s], ks * 64, 0);
+    const uint32_t full0 = T::leader_addr(&full[0]);
+    const int brow = static_cast<int>(rank * T::kBRows);
+    uint32_t it = 0;
+    int i = 0;
+    auto load_wf = [&]() {
+      for (int ks = 0; ks < 4; ++ks, ++it) {
+        const int s = it % T::kStages;
+        mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 11);
+        if (elect_one()) {
+          T::expect_leader(full0 + 8 * s, T::kBBytes);
+          T::load2(stage_base + s * T::kStageBytes + kABytes, &tm_wf, full0 + 8 * s, ks * 64, brow);
         }
-      };
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
-        const int b = tile / a.tiles_per_clip;
-        const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
-        for (int ks = 0; ks < total_ks; ++ks, ++it) {
-          if (ks == J && i > 0) load_wf();
-          const int s = it % kStages;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 12);
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          uint8_t* sa = stage_base + s * kStageBytes;
-          tma_load_4d(sa, &tm_gate, &full[s], (ks & 3) * 64, l0, b, ks >> 2);
-          tma_load_2d(sa + kABytes, &tm_ws, &full[s], ks * 64, 0);
-        }
+        __syncwarp();
       }
-      if (i > 0) load_wf();
+    };
+    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
+      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+      for (int ks = 0; ks < total_ks; ++ks, ++it) {
+        if (ks == J && i > 0) load_wf();
+        const int s = it % T::kStages;
+        mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 12);
+        if (elect_one()) {
+          T::expect_leader(full0 + 8 * s, T::kStageBytes);
+          uint8_t* sa = stage_base + s * T::kStageBytes;
+          T::load4(sa, &tm_gate, full0 + 8 * s, (ks & 3) * 64, tc.l0, tc.b, ks >> 2);
+          T::load2(sa + kABytes, &tm_ws, full0 + 8 * s, ks * 64, brow);
+        }
+        __syncwarp();
+      }
     }
+    if (i > 0) load_wf();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    if (rank == 0) {
+      const uint64_t desc0 = umma_desc_sw128(smem_u32(stage_base));
+      const uint64_t sdesc0 = umma_desc_sw128(smem_u32(s_tile));
       uint32_t it = 0;
       int i = 0;
       auto head_gemm = [&](int ip) {
         const uint32_t d = tmem_base + ((ip & 1) ? 256u : 0u);
-        mbar_wait(s_ready, ip & 1, 13);
+        T::wait_leader(s_ready, ip & 1, 13);
         tc_fence_after();
         for (int ks = 0; ks < 4; ++ks, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&full[s], (it / kStages) & 1, 14);
+          const int s = it % T::kStages;
+          T::wait_leader(&full[s], (it / T::kStages) & 1, 14);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(s_tile + ks * kABytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(stage_base + s * kStageBytes + kABytes));
+          if (elect_one()) {
+            const uint64_t da = sdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
+            const uint64_t db = desc0 + static_cast<uint64_t>((s * T::kStageBytes + kABytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
-          umma_commit(&empty[s]);
+            for (int k = 0; k < 4; ++k) T::mma(d, da + 2 * k, db + 2 * k, (ks | k) != 0);
+            T::commit(&empty[s]);
+            if (ks == 3) T::commit(&d3_full[ip & 1]);
+          }
+          __syncwarp();
         }
-        umma_commit(&d3_full[ip & 1]);
       };
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
-        const uint32_t p = i & 1, u = i >> 1;
+      for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
+        const uint32_t p = i & 1, uu = i >> 1;
         const uint32_t d = tmem_base + (p ? 256u : 0u);
-        if (u >= 1) {
-          mbar_wait(&d_empty[p], (u - 1) & 1, 15);
+        if (uu >= 1) {
+          T::wait_leader(&d_empty[p], (uu - 1) & 1, 15);
           tc_fence_after();
         }
         for (int ks = 0; ks < total_ks; ++ks, ++it) {
           if (ks == J && i > 0) head_gemm(i - 1);
-          const int s = it % kStages;
-          mbar_wait(&full[s], (it / kStages) & 1, 16);
+          const int s = it % T::kStages;
+          T::wait_leader(&full[s], (it / T::kStages) & 1, 16);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + s * kStageBytes);
-          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
+          if (elect_one()) {
+            const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
+            const uint64_t db = da + static_cast<uint64_t>(kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
-          umma_commit(&empty[s]);
+            for (int k = 0; k < 4; ++k) T::mma(d, da + 2 * k, db + 2 * k, (ks | k) != 0);
+            T::commit(&empty[s]);
+            if (ks == total_ks - 1) T::commit(&d_full[p]);
+          }
+          __syncwarp();
         }
-        umma_commit(&d_full[p]);
       }
       if (i > 0) head_gemm(i - 1);
     }
@@ -523,16 +661,18 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
     const int hh = e >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_ready_l = T::leader_addr(s_ready);
+    const uint32_t d_empty0 = T::leader_addr(&d_empty[0]);
     int i = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++i) {
-      const uint32_t p = i & 1, u = i >> 1;
-      const int b = tile / a.tiles_per_clip;
-      const int l0 = (tile - b * a.tiles_per_clip) * kTileT;
+    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
+      const uint32_t p = i & 1, uu = i >> 1;
+      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+      const int b = tc.b, l0 = tc.l0;
       const uint32_t buf = tmem_base + (p ? 256u : 0u) + lane_addr;
       const bool row_ok = (l0 + row) < a.L;
 
       // ---- skip sum -> bf16 operand tile ----
-      mbar_wait(&d_full[p], u & 1, 17);
+      mbar_wait(&d_full[p], uu & 1, 17);
       tc_fence_after();
 #pragma unroll 1
       for (int itn = 0; itn < 4; ++itn) {
@@ -555,10 +695,10 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_ready);
+      if (lane == 0) T::arrive_leader(s_ready_l);
 
       // ---- head: relu, 256 -> 1 dot ----
-      mbar_wait(&d3_full[p], u & 1, 18);
+      mbar_wait(&d3_full[p], uu & 1, 18);
       tc_fence_after();
       float acc = 0.f;
 #pragma unroll 1
@@ -573,7 +713,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
       partial[(p * 2 + hh) * 128 + row] = acc;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&d_empty[p]);
+      if (lane == 0) T::arrive_leader(d_empty0 + 8 * p);
       named_bar_sync(1, kEpiThreads);
       if (hh == 0 && row_ok) {
         const float eps = partial[(p * 2) * 128 + row] + partial[(p * 2 + 1) * 128 + row] + a.bo;
@@ -594,10 +734,10 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  T::block_sync();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    T::tmem_free(tmem_base);
   }
 }
 
@@ -610,6 +750,7 @@ debug_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   int K) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
+  constexpr uint32_t kStageBytes = kABytes + 256 * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStageBytes);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -1,0 +1,305 @@
+"""Benchmark of the purification hot path (BASELINE.json metric: purified 1-s clips/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE configs[1] -- DDPM t*=2 purification of a batch of 64 synthetic
+1-s 16 kHz clips through the 36-layer DiffWave, then log-mel and the ResNeXt-29 8x64 classifier, bf16
+tensor cores.  One process per GPU; with N > 1 every rank purifies its own 64 clips (weak scaling, no
+collective on the data path) and `value` = clips of all ranks / max-over-ranks device time.
+
+A "step" = one pass over one batch.  `value` has the batch resident in HBM; `e2e` goes through the public
+API (AcousticSystem.forward) from pinned HOST memory and reads the predictions back, copies inside the
+timed region.  `roofline` describes the dominant kernel (the fused residual-layer kernel, 36 launches per
+network evaluation) timed with CUDA events on its own stream during the timed region (ap_profile_*).
+`cpu_baseline` / `--impl reference`: the oracle port of the reference's fp32 CPU path on this box's host
+cores, on a bounded sample (the reference is Python and cannot travel to the GPU box).
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64
+T_STAR = 2
+CLIP_LEN = 16000
+LAYER_GFLOP_PER_CLIP = (2 * 512 * 768 * 16000 + 2 * 256 * 256 * 16000) / 1e9  # conv 12.58 + res 2.10
+FALLBACK_PEAK_TFLOPS = 1590.0  # B200_PROFILING.md fallback (burst); sustained ~1400
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--t-star", type=int, default=T_STAR)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-clips", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks --
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    return FALLBACK_PEAK_TFLOPS, "fallback (B200_PROFILING.md)"
+
+
+# -------------------------------------------------------------------------------- CPU reference arm --
+def cpu_reference_step(n_clips, t_star, state):
+    """One bounded sample of the reference's CPU path (oracle port, fp32, all host threads):
+    DDPM t* purify -> log-mel -> ResNeXt-29 on n_clips clips."""
+    import torch
+    from oracle import mel as o_mel, purify as o_purify, resnext as o_resnext, schedule as o_schedule, \
+        wavenet as o_wavenet, weights as W
+
+    if not state:
+        torch.set_num_threads(os.cpu_count())
+        state["sd"] = W.make_state_dict(1234)
+        state["csd"] = o_resnext.make_state_dict(4321)
+        state["hp"] = o_schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+        state["x"] = W.make_waveforms(n_clips, CLIP_LEN, seed=0)
+        state["z"] = W.make_noise((t_star, n_clips, 1, CLIP_LEN), seed=7)
+    sd = state["sd"]
+    with torch.no_grad():
+        y = o_purify.ddpm_purify(state["hp"], lambda xx, t: o_wavenet.eps_theta(sd, xx, t), state["x"], t_star, state["z"])
+        logits = o_resnext.forward(state["csd"], o_mel.log_mel(y))
+    return logits.argmax(1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    state = {}
+    n = args.cpu_sample_clips
+    for _ in range(args.warmup):
+        cpu_reference_step(n, args.t_star, state)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(n, args.t_star, state)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = "%d clip(s) per step: DDPM t*=%d purify + log-mel + ResNeXt-29, fp32, oracle port of the reference" % (n, args.t_star)
+    line = {
+        "impl": "reference", "metric": "purified 1-s clips/sec", "value": value, "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        "workload": "BASELINE configs[1]: DDPM t*=%d purification + log-mel + ResNeXt-29 8x64, batch %d synthetic "
+                    "1-s 16 kHz clips per GPU, DiffWave-unconditional (36 layers, 256 ch, T=200), random-init weights"
+                    % (args.t_star, args.batch),
+        "batch_per_gpu": args.batch, "t_star": args.t_star, "clip_samples": CLIP_LEN,
+        "l2": "no flush needed: every step streams a ~20 GB activation workspace, far larger than the 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------ our arm --
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import audiopure_b200 as ap
+    from oracle import resnext as o_resnext, weights as W  # seeded random-init checkpoints only (no compute)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
+    model.load_state_dict(W.make_state_dict(1234))
+    model = model.to(dev).eval()
+    hp = ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    defender = ap.DiffWave(model, hp, reverse_timestep=args.t_star, seed=rank)
+    clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
+    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    clf = clf.to(dev).eval()
+    system = ap.AcousticSystem(classifier=clf, transform=ap.LogMelSpectrogram().to(dev), defender=defender)
+    eng = model.engine()
+
+    B = args.batch
+    x_host = W.make_waveforms(B, CLIP_LEN, seed=rank).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def step_resident():
+        with torch.no_grad():
+            return system(x_dev).max(1)[1]
+
+    def step_e2e():
+        with torch.no_grad():
+            xd = x_host.to(dev, non_blocking=True)
+            return system(xd).max(1)[1].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    eng.profile_read()
+    ms = timed(step_resident, args.steps)
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    total_clips = B * world * args.steps
+    value = total_clips / (ms * 1e-3)
+    layer_ms, layer_n = prof["layer"]
+    evals_per_step = args.t_star * ((B + model.max_chunk - 1) // model.max_chunk)
+    launches_per_step = (1 + evals_per_step * (model.num_res_layers + 2)) + ((B + model.max_chunk - 1) // model.max_chunk - 1) + 1
+    peak, peak_src = measured_peak()
+    clips_per_launch = min(B, model.max_chunk)
+    achieved = clips_per_launch * LAYER_GFLOP_PER_CLIP / (layer_ms / max(layer_n, 1)) if layer_n else 0.0  # GFLOP/ms = TFLOP/s
+
+    line = {
+        "metric": "purified 1-s clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": total_clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": B * CLIP_LEN * 4, "d2h_bytes_per_step": B * 8,
+                "api": "AcousticSystem(classifier, LogMelSpectrogram, DiffWave).forward on pinned host waveforms -> argmax on host"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {
+            "kernel": "ap::layer_kernel (fused residual layer: dilated conv GEMM + gate + res GEMM), %d launches per step"
+                      % (evals_per_step * model.num_res_layers),
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak if peak else None, "peak_source": peak_src,
+            "flop_per_launch": clips_per_launch * LAYER_GFLOP_PER_CLIP * 1e9,
+            "avg_launch_ms": layer_ms / max(layer_n, 1), "launches_timed": layer_n,
+            "share_of_step": layer_ms / ms if ms else None,
+            "tail_kernel_ms_per_launch": prof["tail"][0] / max(prof["tail"][1], 1),
+            "traffic": None,
+        },
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            state = {}
+            n = args.cpu_sample_clips
+            cpu_reference_step(n, args.t_star, state)  # warm-up
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                cpu_reference_step(n, args.t_star, state)
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {
+                "value": n / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                "sample": "%d clip(s), DDPM t*=%d purify + log-mel + ResNeXt-29, fp32 oracle port, 1 warm-up + %d timed"
+                          % (n, args.t_star, reps)}
+        traffic_file = os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")
+        if os.path.exists(traffic_file):
+            line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

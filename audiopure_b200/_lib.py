@@ -14,7 +14,6 @@ c_i32_p = ctypes.POINTER(ctypes.c_int32)
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 
 AP_ABI_VERSION = 2
-AP_FLAG_SINGLE_CTA = 1
 AP_COMM_ID_BYTES = 128
 
 

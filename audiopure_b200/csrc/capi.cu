@@ -82,7 +82,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct ap_net {
   int layers = 0, cycle = 0, T = 0, max_chunk = 64;
-  bool pair = true;  // CTA-pair (cta_group::2) kernels
+  std::vector<float> h_b1, h_c2;  // host copies of the bias tables (passed to the layer kernel by value)
   ap_weights w{};
   std::vector<float> alpha, alpha_bar, sigma, sde_beta, sde_acp;
   CUtensorMap tm_w1, tm_w2, tm_ws, tm_wf;
@@ -90,7 +90,7 @@ struct ap_net {
   // activation maps, rebuilt when (workspace, Bc, L) changes
   const void* cached_ws = nullptr;
   int cached_B = 0, cached_L = 0;
-  CUtensorMap tm_h[2], tm_gate;
+  CUtensorMap tm_h[2], tm_h_st[2], tm_gate, tm_gate_st;  // loads use [128-row] boxes, epilogue stores [32-row]
   // measurement hook (ap_profile_*)
   bool profile = false;
   struct Span {
@@ -162,13 +162,15 @@ int ensure_maps(ap_net* n, uint8_t* ws, int Bc, int L) {
   const WsLayout w = ws_layout(n, Bc, L);
   const uint64_t d3[3] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc)};
   for (int i = 0; i < 2; ++i)
-    if (make_map(&n->tm_h[i], ws + w.off_h[i], 3, d3, ap::kTileT)) return 1;
+    if (make_map(&n->tm_h[i], ws + w.off_h[i], 3, d3, ap::kTileT) || make_map(&n->tm_h_st[i], ws + w.off_h[i], 3, d3, 32))
+      return 1;
   const uint64_t d4[4] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc),
                           static_cast<uint64_t>(n->layers)};
   // gate[layer] slabs are h_bytes apart; h_bytes == Bc*L*512 whenever that is a multiple of 1024
   if (w.h_bytes != static_cast<size_t>(Bc) * L * ap::kC * 2)
     return fail("internal: B*L must be even so that layer slabs are contiguous");
-  if (make_map(&n->tm_gate, ws + w.off_gate, 4, d4, ap::kTileT)) return 1;
+  if (make_map(&n->tm_gate, ws + w.off_gate, 4, d4, ap::kTileT) || make_map(&n->tm_gate_st, ws + w.off_gate, 4, d4, 32))
+    return 1;
   n->cached_ws = ws;
   n->cached_B = Bc;
   n->cached_L = L;
@@ -194,46 +196,25 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   }
   const int tiles_per_clip = (L + ap::kTileT - 1) / ap::kTileT;
   const int num_tiles = tiles_per_clip * Bc;
-  // persistent grid: one CTA per SM, or one CTA pair (cluster of 2) per TPC
-  int grid;
-  if (n->pair) {
-    const int units = (num_tiles + 1) / 2, clusters = n->num_sms / 2;
-    grid = 2 * (units < clusters ? units : clusters);
-  } else {
-    grid = num_tiles < n->num_sms ? num_tiles : n->num_sms;
-  }
-  cudaLaunchConfig_t lc{};
-  cudaLaunchAttribute cluster_attr{};
-  cluster_attr.id = cudaLaunchAttributeClusterDimension;
-  cluster_attr.val.clusterDim.x = 2;
-  cluster_attr.val.clusterDim.y = 1;
-  cluster_attr.val.clusterDim.z = 1;
-  lc.gridDim = dim3(grid);
-  lc.blockDim = dim3(ap::kThreads);
-  lc.stream = st;
-  lc.attrs = &cluster_attr;
-  lc.numAttrs = 1;
+  // persistent grid of CTA pairs (clusters of 2, one per TPC); each pair walks pairs of tiles
+  const int units = (num_tiles + 1) / 2, clusters = n->num_sms / 2;
+  const int grid = 2 * (units < clusters ? units : clusters);
+  static const int dbg = getenv("AP_DEBUG") ? atoi(getenv("AP_DEBUG")) : 0;
   for (int l = 0; l < n->layers; ++l) {
     ap::LayerArgs a;
-    a.b1 = n->w.b1 + static_cast<size_t>(l) * 512;
-    a.c2 = n->w.c2 + (static_cast<size_t>(t) * n->layers + l) * ap::kC;
-    a.h_in = h[l & 1];
-    a.h_out = h[(l + 1) & 1];
-    a.B = Bc;
     a.L = L;
     a.tiles_per_clip = tiles_per_clip;
     a.num_tiles = num_tiles;
     a.dilation = 1 << (l % n->cycle);
     a.layer = l;
     a.write_h = (l + 1 < n->layers) ? 1 : 0;
+    a.debug = dbg;
+    ap::LayerBias bias;
+    memcpy(bias.b1, n->h_b1.data() + static_cast<size_t>(l) * 512, sizeof(bias.b1));
+    memcpy(bias.c2, n->h_c2.data() + (static_cast<size_t>(t) * n->layers + l) * ap::kC, sizeof(bias.c2));
     ProfSpan span(n, st, 0);
-    if (n->pair) {
-      lc.dynamicSmemBytes = ap::Tc<true>::kLayerSmem;
-      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<true>, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate, a));
-    } else {
-      ap::layer_kernel<false><<<grid, ap::kThreads, ap::Tc<false>::kLayerSmem, st>>>(n->tm_h[l & 1], n->tm_w1, n->tm_w2,
-                                                                                     n->tm_gate, a);
-    }
+    ap::layer_kernel<<<grid, ap::kThreads, ap::Tc::kLayerSmem, st>>>(n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
+                                                                     n->tm_h_st[(l + 1) & 1], bias, a);
   }
   tail.bs = n->w.bs;
   tail.bf = n->w.bf;
@@ -246,12 +227,7 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   tail.num_layers = n->layers;
   {
     ProfSpan span(n, st, 1);
-    if (n->pair) {
-      lc.dynamicSmemBytes = ap::Tc<true>::kTailSmem;
-      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<true>, n->tm_gate, n->tm_ws, n->tm_wf, tail));
-    } else {
-      ap::tail_kernel<false><<<grid, ap::kThreads, ap::Tc<false>::kTailSmem, st>>>(n->tm_gate, n->tm_ws, n->tm_wf, tail);
-    }
+    ap::tail_kernel<<<grid, ap::kThreads, ap::Tc::kTailSmem, st>>>(n->tm_gate, n->tm_ws, n->tm_wf, tail);
   }
   AP_CUDA(cudaGetLastError());
   return 0;
@@ -351,7 +327,7 @@ int ap_create(const ap_config* cfg, const ap_weights* w, ap_net** out) {
   n->cycle = cfg->dilation_cycle;
   n->T = cfg->T;
   n->max_chunk = cfg->max_chunk > 0 ? cfg->max_chunk : 64;
-  n->pair = (cfg->flags & AP_FLAG_SINGLE_CTA) == 0;
+  AP_CHECK(cfg->flags == 0, "unknown ap_config.flags");
   n->w = *w;
   n->alpha.assign(cfg->alpha, cfg->alpha + cfg->T);
   n->alpha_bar.assign(cfg->alpha_bar, cfg->alpha_bar + cfg->T);
@@ -362,22 +338,24 @@ int ap_create(const ap_config* cfg, const ap_weights* w, ap_net** out) {
   n->device = dev;
   const uint64_t L = static_cast<uint64_t>(n->layers);
   const uint64_t dw1[2] = {768, L * 512}, dw2[2] = {256, L * 256}, dws[2] = {L * 256, 256}, dwf[2] = {256, 256};
-  const uint32_t brows = n->pair ? 128 : 256;  // weight rows staged per CTA per K step
+  const uint32_t brows = ap::Tc::kBRows;  // weight rows staged per CTA per K step (half of N = 256)
   int rc = make_map(&n->tm_w1, w->w1, 2, dw1, brows) || make_map(&n->tm_w2, w->w2, 2, dw2, brows) ||
            make_map(&n->tm_ws, w->ws, 2, dws, brows) || make_map(&n->tm_wf, w->wf, 2, dwf, brows);
   if (rc) {
     delete n;
     return 1;
   }
+  n->h_b1.resize(static_cast<size_t>(n->layers) * 512);
+  n->h_c2.resize(static_cast<size_t>(n->T) * n->layers * ap::kC);
   cudaError_t es[4] = {
-      cudaFuncSetAttribute(ap::layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<false>::kLayerSmem),
-      cudaFuncSetAttribute(ap::tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<false>::kTailSmem),
-      cudaFuncSetAttribute(ap::layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<true>::kLayerSmem),
-      cudaFuncSetAttribute(ap::tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc<true>::kTailSmem)};
+      cudaMemcpy(n->h_b1.data(), w->b1, n->h_b1.size() * sizeof(float), cudaMemcpyDeviceToHost),
+      cudaMemcpy(n->h_c2.data(), w->c2, n->h_c2.size() * sizeof(float), cudaMemcpyDeviceToHost),
+      cudaFuncSetAttribute(ap::layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc::kLayerSmem),
+      cudaFuncSetAttribute(ap::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc::kTailSmem)};
   for (cudaError_t e : es)
     if (e != cudaSuccess) {
       delete n;
-      return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e));
+      return fail(std::string("ap_create: copying bias tables / raising the shared-memory limit: ") + cudaGetErrorString(e));
     }
   *out = n;
   return 0;

@@ -21,7 +21,7 @@ constexpr int kC = 256;          // residual / skip / gate channels (the only wi
 constexpr int kTileT = 128;      // time steps per tile = UMMA M
 constexpr uint32_t kABytes = kTileT * 128;  // [128 rows x 64 bf16]: one K step of activations
 constexpr uint32_t kTileBytes = kTileT * kC * 2;  // a full [128 x 256] bf16 operand tile (4 swizzled sub-tiles)
-constexpr int kThreads = 384;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-3: idle, warps 4-11: epilogue
+constexpr int kThreads = 384;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warp 2: x loads (layer kernel), warp 3: idle, warps 4-11: epilogue
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kTmemCols = 512;
@@ -102,100 +102,32 @@ __global__ void __launch_bounds__(256) prologue_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Shared plumbing of the two tensor-core kernels.  kPair = false: one CTA per 128-step tile, tcgen05
-// cta_group::1 (M = 128).  kPair = true: a cluster of two CTAs (the two SMs of a TPC) per pair of tiles,
-// cta_group::2 (M = 256): each CTA stages its own 128 activation rows and HALF of the weight rows, the
-// leader CTA issues the MMAs for both, each CTA's TMEM receives its own tile's accumulators and each CTA runs
-// its own epilogue.  Per SM this halves the weight bytes written into shared memory and the weight bytes the
-// tensor core reads back out of it -- shared-memory bandwidth, not the tensor pipe, is what caps the 1-CTA form.
+// Shared plumbing of the two tensor-core kernels.
+//
+// Both run as CTA PAIRS: a cluster of two CTAs (the two SMs of a TPC) per pair of 128-step tiles, tcgen05
+// cta_group::2 (M = 256).  Each CTA stages its own 128 activation rows and HALF of the weight rows, the
+// leader CTA (cluster rank 0) issues the MMAs for both, each CTA's TMEM receives its own tile's accumulators
+// and each CTA runs its own epilogue.  Versus one CTA per tile this halves the weight bytes written into
+// each SM's shared memory and the weight bytes the tensor core reads back out of it -- shared-memory
+// bandwidth (128 B/clk/SM), not the tensor pipe, is what caps the single-CTA form (measured 0.95 ms vs
+// 0.87 ms per layer launch at B = 64 before the epilogue rework).
 // ---------------------------------------------------------------------------------------------------
-template <bool kPair>
 struct Tc {
-  static constexpr int kStages = kPair ? 4 : 3;              // TMA -> MMA ring depth
-  static constexpr uint32_t kBRows = kPair ? 128 : 256;      // weight rows staged per CTA per K step
+  static constexpr int kStages = 4;                 // TMA -> MMA ring depth
+  static constexpr uint32_t kBRows = 128;           // weight rows staged per CTA per K step (half of N = 256)
   static constexpr uint32_t kBBytes = kBRows * 128;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kRing = kStages * kStageBytes;
-  static constexpr uint32_t kCtas = kPair ? 2 : 1;
-  static constexpr uint32_t kEpiArrivals = kCtas * (kEpiThreads / 32);  // epilogue -> MMA barrier arrival count
-  static constexpr uint32_t kIdesc = umma_idesc_bf16(kPair ? 256 : 128, 256);
-  static constexpr uint32_t kLayerSmem = kRing + kTileBytes + 512 * 4 + 256 * 4 + 32 * 8 + 1024;
+  static constexpr uint32_t kEpiWarps = kEpiThreads / 32;
+  static constexpr uint32_t kIdesc = umma_idesc_bf16(256, 256);
+  static constexpr uint32_t kXSlotBytes = kABytes;  // one [128 x 64] chunk of the layer input (residual term)
+  static constexpr uint32_t kLayerSmem = kRing + kTileBytes + 2 * kXSlotBytes + 32 * 8 + 1024;
   static constexpr uint32_t kTailSmem = kRing + kTileBytes + 3 * 256 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 1024;
-
-  // Barrier the LEADER's MMA thread waits on: returns the address every CTA of the pair should arrive at.
-  static __device__ __forceinline__ uint32_t leader_addr(uint64_t* bar) {
-    if constexpr (kPair) return mapa_u32(bar, 0);
-    else return smem_u32(bar);
-  }
-  static __device__ __forceinline__ void arrive_leader(uint32_t addr) {
-    if constexpr (kPair) mbar_arrive_cluster(addr);
-    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
-  }
-  static __device__ __forceinline__ void expect_leader(uint32_t addr, uint32_t bytes) {
-    if constexpr (kPair) mbar_arrive_expect_tx_cluster(addr, bytes);
-    else asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
-  }
-  static __device__ __forceinline__ void wait_leader(uint64_t* bar, uint32_t parity, int tag) {
-    mbar_wait(bar, parity, tag);
-  }
-  static __device__ __forceinline__ void load2(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
-    if constexpr (kPair) tma_load_2d_pair(dst, m, bar, c0, c1);
-    else
-      asm volatile(
-          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-              "r"(smem_u32(dst)),
-          "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
-          : "memory");
-  }
-  static __device__ __forceinline__ void load3(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
-    if constexpr (kPair) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
-    else
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
-          "[%2];" ::"r"(smem_u32(dst)),
-          "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-          : "memory");
-  }
-  static __device__ __forceinline__ void load4(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
-                                               int c3) {
-    if constexpr (kPair) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
-    else
-      asm volatile(
-          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-          "[%2];" ::"r"(smem_u32(dst)),
-          "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-          : "memory");
-  }
-  static __device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-    if constexpr (kPair) umma_bf16_pair(d, da, db, kIdesc, acc);
-    else umma_bf16(d, da, db, kIdesc, acc);
-  }
-  static __device__ __forceinline__ void commit(uint64_t* bar) {
-    if constexpr (kPair) umma_commit_pair(bar);
-    else umma_commit(bar);
-  }
-  static __device__ __forceinline__ void block_sync() {  // every thread of the CTA (pair: of both CTAs)
-    if constexpr (kPair) cluster_sync_all();
-    else __syncthreads();
-  }
-  static __device__ __forceinline__ void tmem_allocate(uint32_t* dst) {
-    if constexpr (kPair) {
-      tmem_alloc_pair(dst, kTmemCols);
-      tmem_relinquish_pair();
-    } else {
-      tmem_alloc(dst, kTmemCols);
-      tmem_relinquish();
-    }
-  }
-  static __device__ __forceinline__ void tmem_free(uint32_t addr) {
-    if constexpr (kPair) tmem_dealloc_pair(addr, kTmemCols);
-    else tmem_dealloc(addr, kTmemCols);
-  }
 };
 
-// Work distribution shared by all warp roles: unit u covers tiles [u*kCtas, u*kCtas + kCtas); this CTA takes
-// tile u*kCtas + rank.  A pair whose second tile does not exist gives that CTA an all-out-of-bounds tile
-// (TMA zero-fills its loads, its stores are masked) so that both CTAs walk identical barrier sequences.
+// Work distribution shared by all warp roles: unit u covers tiles 2u and 2u+1; this CTA takes tile 2u + rank.
+// A pair whose second tile does not exist gives that CTA an all-out-of-bounds tile (TMA zero-fills its loads
+// and clips its stores) so that both CTAs walk identical barrier sequences.
 struct TileCoord {
   int b, l0;
   bool valid;
@@ -214,7 +146,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_tiles, int til
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1: one residual layer (WaveNet.py:75-97), fully fused, persistent over 128-step tiles.
+// K1: one residual layer (WaveNet.py:75-97), fully fused, persistent over pairs of 128-step tiles.
 //
 //   GEMM1  D1[128 x 512] = sum_{tap,c} h[l + (tap-1)d][c] * W1[o][c][tap]     (K = 768)
 //          issued as two N = 256 chunks; chunk c holds gate channels [128c, 128c+128): TMEM columns
@@ -228,85 +160,97 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_tiles, int til
 // TMEM (512 columns): two 256-column buffers X, Y.  For tile parity p: chunk0 -> bufA, chunk1 -> bufB,
 // D2 -> bufA again (its gate half was drained by then), with (bufA, bufB) = (X, Y) for even tiles and
 // (Y, X) for odd tiles, so the MMA warp runs ahead of the epilogue by one chunk at all times.
+//
+// Epilogue data movement is all TMA: the residual input x arrives in two 16 KB slots (loaded by warp 2),
+// the gate tile and h_next leave by TMA stores.  Every epilogue warp (q, hh) owns rows [32q, 32q+32) of the
+// 64-channel sub-tiles {hh, 2+hh} of the 64 KB operand tile for BOTH uses (gate, then h_next staging), and
+// stores its own [32 x 64] boxes, so the eight warps never need a CTA-wide barrier.  (Per-thread 16-byte
+// global accesses at a 512-byte stride cost 0.91 -> 0.56 ms per launch in an ablation; see DESIGN.md.)
 // ---------------------------------------------------------------------------------------------------
 struct LayerArgs {
-  const float* b1;             // [512] conv bias, permuted like W1's rows
-  const float* c2;             // [256] sqrt(.5)*b_res + part_{n+1}(t)
-  const __nv_bfloat16* h_in;   // [B][L][256]
-  __nv_bfloat16* h_out;        // [B][L][256]
-  int B, L, tiles_per_clip, num_tiles;
+  int L, tiles_per_clip, num_tiles;
   int dilation, layer;
-  int write_h;                 // 0 for the last layer (its residual output is never consumed)
+  int write_h;  // 0 for the last layer (its residual output is never consumed)
+  int debug;    // experiment switches (AP_DEBUG env): 2 no MUFU, 4 no h stores, 8 no gate store
+};
+struct LayerBias {  // passed by value: lives in the constant bank, read with warp-uniform indices
+  float b1[512];    // conv bias, permuted like W1's rows
+  float c2[256];    // sqrt(.5)*b_res + part_{n+1}(t)
 };
 
-template <bool kPair>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w1,
-             const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_gate,
+             const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_gate_st,
+             const __grid_constant__ CUtensorMap tm_h_st, const __grid_constant__ LayerBias bias,
              const LayerArgs a) {
-  using T = Tc<kPair>;
+  using T = Tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
-  uint8_t* gate_s = smem + T::kRing;
-  float* b1s = reinterpret_cast<float*>(gate_s + kTileBytes);
-  float* c2s = b1s + 512;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(c2s + 256);
+  uint8_t* gate_s = smem + T::kRing;                 // gate tile, later h_next staging
+  uint8_t* x_s = gate_s + kTileBytes;                // 2 x [128 x 64] slots of the layer input
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + 2 * T::kXSlotBytes);
   uint64_t* full = bars;             // [kStages] TMA -> MMA            (leader's copy is the live one)
   uint64_t* empty = bars + 4;        // [kStages] MMA -> TMA            (per CTA, multicast commit)
   uint64_t* d1_full = bars + 8;      // [2] chunk accumulator ready     MMA -> epilogue (per CTA)
   uint64_t* gate_ready = bars + 10;  // [2] gate half in smem, chunk's TMEM drained   epilogue -> MMA (leader)
   uint64_t* d2_full = bars + 12;     //     residual accumulator ready  MMA -> epilogue (per CTA)
   uint64_t* d2_empty = bars + 13;    //     residual accumulator drained epilogue -> MMA (leader)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* x_full = bars + 14;      // [2] x slot loaded               x producer -> epilogue
+  uint64_t* x_empty = bars + 16;     // [2] x slot consumed             epilogue -> x producer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int units = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const uint32_t rank = cluster_ctarank();
+  const int unit0 = static_cast<int>(blockIdx.x >> 1);
+  const int units = static_cast<int>(gridDim.x >> 1);
 
-  for (int i = threadIdx.x; i < 512; i += kThreads) b1s[i] = a.b1[i];
-  for (int i = threadIdx.x; i < 256; i += kThreads) c2s[i] = a.c2[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < T::kStages; ++s) {
-      mbar_init(&full[s], T::kCtas);
+      mbar_init(&full[s], 2);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(&d1_full[0], 1);
-    mbar_init(&d1_full[1], 1);
-    mbar_init(&gate_ready[0], T::kEpiArrivals);
-    mbar_init(&gate_ready[1], T::kEpiArrivals);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&d1_full[s], 1);
+      mbar_init(&gate_ready[s], 2 * T::kEpiWarps);
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], T::kEpiWarps / 2);
+    }
     mbar_init(d2_full, 1);
-    mbar_init(d2_empty, T::kEpiArrivals);
+    mbar_init(d2_empty, 2 * T::kEpiWarps);
     fence_mbar_init();
     tma_prefetch_desc(&tm_h);
     tma_prefetch_desc(&tm_w1);
     tma_prefetch_desc(&tm_w2);
-    tma_prefetch_desc(&tm_gate);
+    tma_prefetch_desc(&tm_gate_st);
+    tma_prefetch_desc(&tm_h_st);
   }
-  if (warp == 1) T::tmem_allocate(tmem_ptr);
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, kTmemCols);
+    tmem_relinquish_pair();
+  }
   tc_fence_before();
-  T::block_sync();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     // ======================= TMA producer (whole warp walks the loop; one elected lane issues) ==========
-    const uint32_t full0 = T::leader_addr(&full[0]);
+    const uint32_t full0 = mapa_u32(&full[0], 0);
     const int brow = static_cast<int>(rank * T::kBRows);
     uint32_t it = 0;
-    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units) {
-      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+    for (int u = unit0; 2 * u < a.num_tiles; u += units) {
+      const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
       for (int c = 0; c < 2; ++c) {
         for (int ks = 0; ks < 12; ++ks, ++it) {
           const int s = it % T::kStages;
           mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 1);
           if (elect_one()) {
-            T::expect_leader(full0 + 8 * s, T::kStageBytes);
+            mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
             uint8_t* sa = stage_base + s * T::kStageBytes;
             const int tap = ks >> 2;
-            T::load3(sa, &tm_h, full0 + 8 * s, (ks & 3) * 64, tc.l0 + (tap - 1) * a.dilation, tc.b);
-            T::load2(sa + kABytes, &tm_w1, full0 + 8 * s, ks * 64, a.layer * 512 + c * 256 + brow);
+            tma_load_3d_pair(sa, &tm_h, full0 + 8 * s, (ks & 3) * 64, tc.l0 + (tap - 1) * a.dilation, tc.b);
+            tma_load_2d_pair(sa + kABytes, &tm_w1, full0 + 8 * s, ks * 64, a.layer * 512 + c * 256 + brow);
           }
           __syncwarp();
         }
@@ -315,8 +259,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         const int s = it % T::kStages;
         mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 2);
         if (elect_one()) {
-          T::expect_leader(full0 + 8 * s, T::kBBytes);
-          T::load2(stage_base + s * T::kStageBytes + kABytes, &tm_w2, full0 + 8 * s, ks * 64, a.layer * 256 + brow);
+          mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kBBytes);
+          tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_w2, full0 + 8 * s, ks * 64,
+                           a.layer * 256 + brow);
         }
         __syncwarp();
       }
@@ -328,167 +273,198 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       const uint64_t gdesc0 = umma_desc_sw128(smem_u32(gate_s));
       uint32_t it = 0;
       int i = 0;
-      for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
+      for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
         const uint32_t p = i & 1;
         const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
         for (int c = 0; c < 2; ++c) {
           if (c == 1 && i > 0) {  // bufB held the previous tile's residual accumulator
-            T::wait_leader(d2_empty, (i - 1) & 1, 3);
+            mbar_wait(d2_empty, (i - 1) & 1, 3);
             tc_fence_after();
           }
           const uint32_t d = c ? bufB : bufA;
           for (int ks = 0; ks < 12; ++ks, ++it) {
             const int s = it % T::kStages;
-            T::wait_leader(&full[s], (it / T::kStages) & 1, 4);
+            mbar_wait(&full[s], (it / T::kStages) & 1, 4);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
               const uint64_t db = da + static_cast<uint64_t>(kABytes >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) T::mma(d, da + 2 * k, db + 2 * k, (ks | k) != 0);
-              T::commit(&empty[s]);
-              if (ks == 11) T::commit(&d1_full[c]);
+              for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+              umma_commit_pair(&empty[s]);
+              if (ks == 11) umma_commit_pair(&d1_full[c]);
             }
             __syncwarp();
           }
         }
         for (int ks = 0; ks < 4; ++ks, ++it) {
           if (ks == 0 || ks == 2) {  // K 0..127 needs gate half 0 (and bufA drained), K 128..255 half 1
-            T::wait_leader(&gate_ready[ks >> 1], p, 5);
+            mbar_wait(&gate_ready[ks >> 1], p, 5);
             tc_fence_after();
           }
           const int s = it % T::kStages;
-          T::wait_leader(&full[s], (it / T::kStages) & 1, 6);
+          mbar_wait(&full[s], (it / T::kStages) & 1, 6);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = gdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
             const uint64_t db = desc0 + static_cast<uint64_t>((s * T::kStageBytes + kABytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) T::mma(bufA, da + 2 * k, db + 2 * k, (ks | k) != 0);
-            T::commit(&empty[s]);
-            if (ks == 3) T::commit(d2_full);
+            for (int k = 0; k < 4; ++k) umma_bf16_pair(bufA, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+            umma_commit_pair(&empty[s]);
+            if (ks == 3) umma_commit_pair(d2_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ======================= x producer: the layer input again, for the residual term ==================
+    // chunk k (channels [64k, 64k+64)) goes to slot k & 1; warpgroup hh of the epilogue consumes slot hh.
+    int i = 0;
+    for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
+      const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
+      for (int kk = 0; kk < 2; ++kk) {
+        for (int sl = 0; sl < 2; ++sl) {
+          mbar_wait(&x_empty[sl], ((2 * i + kk) & 1) ^ 1, 9);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&x_full[sl], T::kXSlotBytes);
+            tma_load_3d(x_s + sl * T::kXSlotBytes, &tm_h, &x_full[sl], (sl + 2 * kk) * 64, tc.l0, tc.b);
           }
           __syncwarp();
         }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ======================= epilogue (8 warps) =======================
+    // ======================= epilogue (8 warps, each owns rows [32q,+32) of sub-tiles {hh, 2+hh}) ========
     const int e = warp - kEpiWarp0;
     const int q = warp & 3;   // TMEM lane quarter this warp may read
-    const int hh = e >> 2;    // which half of the columns this warpgroup handles
+    const int hh = e >> 2;    // warpgroup: which 64-channel sub-tiles / which half of a gate chunk
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t gate_ready0 = T::leader_addr(&gate_ready[0]);
-    const uint32_t d2_empty_l = T::leader_addr(d2_empty);
+    const uint32_t gate_ready0 = mapa_u32(&gate_ready[0], 0);
+    const uint32_t d2_empty_l = mapa_u32(d2_empty, 0);
     int i = 0;
-    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
+    for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
       const uint32_t p = i & 1;
-      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+      const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
       const int b = tc.b, l0 = tc.l0;
       const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
-      const bool row_ok = (l0 + row) < a.L;
 
-      // ---- gate: two chunks of 128 gate channels ----
+      // this warp's regions are rewritten below: its previous h_next stores must have finished reading them
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+
+      // ---- gate: two chunks of 128 gate channels; this warp does channels [64hh, 64hh+64) of each ----
       for (int c = 0; c < 2; ++c) {
         mbar_wait(&d1_full[c], p, 7);
         tc_fence_after();
         const uint32_t buf = (c ? bufB : bufA) + lane_addr;
-#pragma unroll 1
+        uint8_t* sub = gate_s + (2 * c + hh) * kABytes;  // sub-tile of gate channels [128c + 64hh, +64)
+#pragma unroll
         for (int itn = 0; itn < 2; ++itn) {
           const int j0 = hh * 64 + itn * 32;  // gate channel within the chunk
           uint32_t rt[32], rs[32];
           tmem_ld32(buf + j0, rt);
           tmem_ld32(buf + 128 + j0, rs);
           tmem_ld_wait();
-          const float* bt = b1s + c * 256 + j0;
+          const float* bt = bias.b1 + c * 256 + j0;
           const float* bs = bt + 128;
           uint32_t pk[16];
+          if (a.debug & 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float o0 = tanh_fast(__uint_as_float(rt[2 * j]) + bt[2 * j]) *
-                             sigmoid_fast(__uint_as_float(rs[2 * j]) + bs[2 * j]);
-            const float o1 = tanh_fast(__uint_as_float(rt[2 * j + 1]) + bt[2 * j + 1]) *
-                             sigmoid_fast(__uint_as_float(rs[2 * j + 1]) + bs[2 * j + 1]);
-            pk[j] = pack_bf16x2(o0, o1);
+            for (int j = 0; j < 16; ++j)
+              pk[j] = pack_bf16x2(__uint_as_float(rt[2 * j]) + bt[2 * j] + __uint_as_float(rs[2 * j]) + bs[2 * j],
+                                  __uint_as_float(rt[2 * j + 1]) + bt[2 * j + 1] + __uint_as_float(rs[2 * j + 1]) +
+                                      bs[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float o0 = tanh_fast(__uint_as_float(rt[2 * j]) + bt[2 * j]) *
+                               sigmoid_fast(__uint_as_float(rs[2 * j]) + bs[2 * j]);
+              const float o1 = tanh_fast(__uint_as_float(rt[2 * j + 1]) + bt[2 * j + 1]) *
+                               sigmoid_fast(__uint_as_float(rs[2 * j + 1]) + bs[2 * j + 1]);
+              pk[j] = pack_bf16x2(o0, o1);
+            }
           }
-          const int gc = c * 128 + j0;  // first gate channel of these 32
-          uint8_t* sub = gate_s + (gc >> 6) * kABytes;
-          const int q0 = (gc & 63) >> 3;
 #pragma unroll
           for (int v = 0; v < 4; ++v)
-            *reinterpret_cast<uint4*>(sub + sw128_offset(row, q0 + v)) =
+            *reinterpret_cast<uint4*>(sub + sw128_offset(row, itn * 4 + v)) =
                 make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) T::arrive_leader(gate_ready0 + 8 * c);
+        if (lane == 0) {
+          mbar_arrive_cluster(gate_ready0 + 8 * c);
+          // this warp's [32 x 64] box of the gate tile -> HBM (operand of the tail's skip GEMM)
+          if (!(a.debug & 8)) {
+            tma_store_4d(&tm_gate_st, sub + q * 32 * 128, (2 * c + hh) * 64, l0 + q * 32, b, a.layer);
+            tma_store_commit();
+          }
+        }
       }
 
-      // ---- gate tile -> HBM (operand of the tail's skip GEMM) ----
-      named_bar_sync(1, kEpiThreads);
-      if (e == 0 && lane == 0 && tc.valid) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) tma_store_4d(&tm_gate, gate_s + s * kABytes, s * 64, l0, b, a.layer);
-        tma_store_commit();
-      }
-
-      // ---- residual output (x is prefetched one 32-channel group ahead to hide the load latency) ----
-      const size_t grow = (static_cast<size_t>(b) * a.L + l0 + row) * kC;
-      const uint4* xsrc = reinterpret_cast<const uint4*>(a.h_in + grow + hh * 128);
-      uint4 xn[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) xn[v] = row_ok ? __ldg(xsrc + v) : make_uint4(0, 0, 0, 0);
-      mbar_wait(d2_full, p, 8);
+      // ---- residual output: h_next = sqrt(.5) x + D2 + c2, staged in this warp's regions of the tile ----
+      mbar_wait(d2_full, p, 8);  // also: the MMAs have finished reading the gate tile
       tc_fence_after();
+      if (lane == 0) tma_store_wait_read();  // ... and so have this warp's gate stores
+      __syncwarp();
+#pragma unroll 1
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = hh + 2 * kk;  // 64-channel chunk == sub-tile index
+        mbar_wait(&x_full[hh], (2 * i + kk) & 1, 10);
+        const uint8_t* xs = x_s + hh * T::kXSlotBytes;
+        uint8_t* sub = gate_s + k * kABytes;
 #pragma unroll
-      for (int itn = 0; itn < 4; ++itn) {
-        const int j0 = hh * 128 + itn * 32;
-        uint4 xv[4];
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(bufA + lane_addr + k * 64 + half * 32, r);
+          uint4 xv[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) xv[v] = xn[v];
-        if (itn < 3) {
+          for (int v = 0; v < 4; ++v) xv[v] = *reinterpret_cast<const uint4*>(xs + sw128_offset(row, half * 4 + v));
+          tmem_ld_wait();
+          const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+          const float* cc = bias.c2 + k * 64 + half * 32;
+          uint4 ov[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(ov);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) xn[v] = row_ok ? __ldg(xsrc + (itn + 1) * 4 + v) : make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 16; ++j) {
+            const float v0 = fmaf(bf16_lo(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j]) + cc[2 * j]);
+            const float v1 = fmaf(bf16_hi(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j + 1]) + cc[2 * j + 1]);
+            ow[j] = pack_bf16x2(v0, v1);
+          }
+#pragma unroll
+          for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(sub + sw128_offset(row, half * 4 + v)) = ov[v];
         }
-        uint32_t r[32];
-        tmem_ld32(bufA + lane_addr + j0, r);
-        tmem_ld_wait();
-        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
-        uint4 ov[4];
-        uint32_t* ow = reinterpret_cast<uint32_t*>(ov);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float v0 = fmaf(bf16_lo(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j]) + c2s[j0 + 2 * j]);
-          const float v1 = fmaf(bf16_hi(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j + 1]) + c2s[j0 + 2 * j + 1]);
-          ow[j] = pack_bf16x2(v0, v1);
-        }
-        if (row_ok && a.write_h) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) reinterpret_cast<uint4*>(a.h_out + grow + j0)[v] = ov[v];
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_empty[hh]);
       }
       tc_fence_before();
+      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) T::arrive_leader(d2_empty_l);
-      // the gate tile in smem is rewritten by the next tile: its TMA store must have finished reading it
-      if (e == 0 && lane == 0) tma_store_wait_read();
-      named_bar_sync(1, kEpiThreads);
+      if (lane == 0) {
+        mbar_arrive_cluster(d2_empty_l);
+        if (a.write_h && !(a.debug & 4)) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            tma_store_3d(&tm_h_st, gate_s + (hh + 2 * kk) * kABytes + q * 32 * 128, (hh + 2 * kk) * 64, l0 + q * 32, b);
+          tma_store_commit();
+        }
+      }
     }
-    if (e == 0 && lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  T::block_sync();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    T::tmem_free(tmem_base);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2: skip GEMM + output head + reverse-step update, persistent over 128-step tiles.
+// K2: skip GEMM + output head + reverse-step update, persistent over pairs of 128-step tiles.
 //
 //   GEMMs  S[128 x 256]  = sum_n gate_n * (sqrt(1/N) W_skip,n)^T      (K = N*256; WaveNet.py:95,133,135)
 //   head   y  = relu(bf16(S + bias) * W_f^T + b_f)                     (GEMM, K = 256; WaveNet.py:160-161)
@@ -516,11 +492,10 @@ struct TailArgs {
   int B, L, tiles_per_clip, num_tiles, num_layers;
 };
 
-template <bool kPair>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__ CUtensorMap tm_ws,
             const __grid_constant__ CUtensorMap tm_wf, const TailArgs a) {
-  using T = Tc<kPair>;
+  using T = Tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
@@ -539,9 +514,9 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int units = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const uint32_t rank = cluster_ctarank();
+  const int unit0 = static_cast<int>(blockIdx.x >> 1);
+  const int units = static_cast<int>(gridDim.x >> 1);
 
   for (int i = threadIdx.x; i < 256; i += kThreads) {
     bss[i] = a.bs[i];
@@ -550,23 +525,26 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < T::kStages; ++s) {
-      mbar_init(&full[s], T::kCtas);
+      mbar_init(&full[s], 2);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&d_full[s], 1);
-      mbar_init(&d_empty[s], T::kEpiArrivals);
+      mbar_init(&d_empty[s], 2 * T::kEpiWarps);
       mbar_init(&d3_full[s], 1);
     }
-    mbar_init(s_ready, T::kEpiArrivals);
+    mbar_init(s_ready, 2 * T::kEpiWarps);
     fence_mbar_init();
     tma_prefetch_desc(&tm_gate);
     tma_prefetch_desc(&tm_ws);
     tma_prefetch_desc(&tm_wf);
   }
-  if (warp == 1) T::tmem_allocate(tmem_ptr);
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, kTmemCols);
+    tmem_relinquish_pair();
+  }
   tc_fence_before();
-  T::block_sync();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -574,7 +552,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   const int J = total_ks / 2 < 16 ? total_ks / 2 : 16;  // where the previous tile's head GEMM is slotted in
 
   if (warp == 0) {
-    const uint32_t full0 = T::leader_addr(&full[0]);
+    const uint32_t full0 = mapa_u32(&full[0], 0);
     const int brow = static_cast<int>(rank * T::kBRows);
     uint32_t it = 0;
     int i = 0;
@@ -583,23 +561,23 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         const int s = it % T::kStages;
         mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 11);
         if (elect_one()) {
-          T::expect_leader(full0 + 8 * s, T::kBBytes);
-          T::load2(stage_base + s * T::kStageBytes + kABytes, &tm_wf, full0 + 8 * s, ks * 64, brow);
+          mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kBBytes);
+          tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_wf, full0 + 8 * s, ks * 64, brow);
         }
         __syncwarp();
       }
     };
-    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
-      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+    for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
+      const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
       for (int ks = 0; ks < total_ks; ++ks, ++it) {
         if (ks == J && i > 0) load_wf();
         const int s = it % T::kStages;
         mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 12);
         if (elect_one()) {
-          T::expect_leader(full0 + 8 * s, T::kStageBytes);
+          mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
           uint8_t* sa = stage_base + s * T::kStageBytes;
-          T::load4(sa, &tm_gate, full0 + 8 * s, (ks & 3) * 64, tc.l0, tc.b, ks >> 2);
-          T::load2(sa + kABytes, &tm_ws, full0 + 8 * s, ks * 64, brow);
+          tma_load_4d_pair(sa, &tm_gate, full0 + 8 * s, (ks & 3) * 64, tc.l0, tc.b, ks >> 2);
+          tma_load_2d_pair(sa + kABytes, &tm_ws, full0 + 8 * s, ks * 64, brow);
         }
         __syncwarp();
       }
@@ -613,42 +591,42 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
       int i = 0;
       auto head_gemm = [&](int ip) {
         const uint32_t d = tmem_base + ((ip & 1) ? 256u : 0u);
-        T::wait_leader(s_ready, ip & 1, 13);
+        mbar_wait(s_ready, ip & 1, 13);
         tc_fence_after();
         for (int ks = 0; ks < 4; ++ks, ++it) {
           const int s = it % T::kStages;
-          T::wait_leader(&full[s], (it / T::kStages) & 1, 14);
+          mbar_wait(&full[s], (it / T::kStages) & 1, 14);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = sdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
             const uint64_t db = desc0 + static_cast<uint64_t>((s * T::kStageBytes + kABytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) T::mma(d, da + 2 * k, db + 2 * k, (ks | k) != 0);
-            T::commit(&empty[s]);
-            if (ks == 3) T::commit(&d3_full[ip & 1]);
+            for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+            umma_commit_pair(&empty[s]);
+            if (ks == 3) umma_commit_pair(&d3_full[ip & 1]);
           }
           __syncwarp();
         }
       };
-      for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
+      for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
         const uint32_t p = i & 1, uu = i >> 1;
         const uint32_t d = tmem_base + (p ? 256u : 0u);
         if (uu >= 1) {
-          T::wait_leader(&d_empty[p], (uu - 1) & 1, 15);
+          mbar_wait(&d_empty[p], (uu - 1) & 1, 15);
           tc_fence_after();
         }
         for (int ks = 0; ks < total_ks; ++ks, ++it) {
           if (ks == J && i > 0) head_gemm(i - 1);
           const int s = it % T::kStages;
-          T::wait_leader(&full[s], (it / T::kStages) & 1, 16);
+          mbar_wait(&full[s], (it / T::kStages) & 1, 16);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
             const uint64_t db = da + static_cast<uint64_t>(kABytes >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) T::mma(d, da + 2 * k, db + 2 * k, (ks | k) != 0);
-            T::commit(&empty[s]);
-            if (ks == total_ks - 1) T::commit(&d_full[p]);
+            for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+            umma_commit_pair(&empty[s]);
+            if (ks == total_ks - 1) umma_commit_pair(&d_full[p]);
           }
           __syncwarp();
         }
@@ -661,12 +639,12 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
     const int hh = e >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t s_ready_l = T::leader_addr(s_ready);
-    const uint32_t d_empty0 = T::leader_addr(&d_empty[0]);
+    const uint32_t s_ready_l = mapa_u32(s_ready, 0);
+    const uint32_t d_empty0 = mapa_u32(&d_empty[0], 0);
     int i = 0;
-    for (int u = unit0; u * static_cast<int>(T::kCtas) < a.num_tiles; u += units, ++i) {
+    for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
       const uint32_t p = i & 1, uu = i >> 1;
-      const TileCoord tc = tile_coord(u * T::kCtas + rank, a.num_tiles, a.tiles_per_clip);
+      const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
       const int b = tc.b, l0 = tc.l0;
       const uint32_t buf = tmem_base + (p ? 256u : 0u) + lane_addr;
       const bool row_ok = (l0 + row) < a.L;
@@ -695,7 +673,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) T::arrive_leader(s_ready_l);
+      if (lane == 0) mbar_arrive_cluster(s_ready_l);
 
       // ---- head: relu, 256 -> 1 dot ----
       mbar_wait(&d3_full[p], uu & 1, 18);
@@ -713,7 +691,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
       partial[(p * 2 + hh) * 128 + row] = acc;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) T::arrive_leader(d_empty0 + 8 * p);
+      if (lane == 0) mbar_arrive_cluster(d_empty0 + 8 * p);
       named_bar_sync(1, kEpiThreads);
       if (hh == 0 && row_ok) {
         const float eps = partial[(p * 2) * 128 + row] + partial[(p * 2 + 1) * 128 + row] + a.bo;
@@ -734,10 +712,10 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   }
 
   tc_fence_before();
-  T::block_sync();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    T::tmem_free(tmem_base);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 

@@ -80,7 +80,7 @@ class WaveNet_Speech_Commands(nn.Module):
 
     def __init__(self, in_channels=1, res_channels=256, skip_channels=128, out_channels=1, num_res_layers=30,
                  dilation_cycle=10, diffusion_step_embed_dim_in=128, diffusion_step_embed_dim_mid=512,
-                 diffusion_step_embed_dim_out=512, diffusion_config=None, max_chunk=64, single_cta=False):
+                 diffusion_step_embed_dim_out=512, diffusion_config=None, max_chunk=64):
         super().__init__()
         if not (in_channels == 1 and out_channels == 1 and res_channels == 256 and skip_channels == 256):
             raise NotImplementedError(
@@ -92,7 +92,6 @@ class WaveNet_Speech_Commands(nn.Module):
         self.embed_dim_in = diffusion_step_embed_dim_in
         self.diffusion_config = dict(diffusion_config or DEFAULT_DIFFUSION_CONFIG)
         self.max_chunk = max_chunk
-        self.single_cta = single_cta  # A/B switch: tcgen05 cta_group::1 kernels instead of CTA pairs
         self.init_conv = nn.Sequential(_Wrap(_WNConv(in_channels, res_channels, 1)))
         self.residual_layer = _Group(res_channels, skip_channels, num_res_layers, diffusion_step_embed_dim_in,
                                      diffusion_step_embed_dim_mid, diffusion_step_embed_dim_out)
@@ -213,7 +212,7 @@ class Engine:
         cfg.dilation_cycle = model.dilation_cycle
         cfg.T = dc["T"]
         cfg.max_chunk = model.max_chunk
-        cfg.flags = _lib.AP_FLAG_SINGLE_CTA if model.single_cta else 0
+        cfg.flags = 0
         for name, t in zip(("alpha", "alpha_bar", "sigma", "sde_beta", "sde_alphas_cumprod"), self._tables):
             setattr(cfg, name, ctypes.cast(t.data_ptr(), _lib.c_float_p))
         w = _lib.ApWeights()

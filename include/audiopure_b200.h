@@ -27,10 +27,6 @@ extern "C" {
 
 #define AP_ABI_VERSION 2
 
-/* ap_config.flags: run the tensor-core kernels as single CTAs (tcgen05 cta_group::1) instead of CTA pairs
- * (cta_group::2).  Same results; kept for A/B measurements. */
-#define AP_FLAG_SINGLE_CTA 1u
-
 typedef struct ap_net ap_net;   /* the packed DiffWave epsilon-network + its diffusion schedule */
 typedef struct ap_comm ap_comm; /* an NCCL communicator for the vote-count all-reduce           */
 
@@ -41,7 +37,7 @@ typedef struct ap_config {
   int32_t dilation_cycle; /* 12 -> dilation 2^(n mod 12), WaveNet.py:116 */
   int32_t T;              /* 200 */
   int32_t max_chunk;      /* clips processed per pass (bounds the workspace); 0 -> 64 */
-  uint32_t flags;         /* AP_FLAG_* */
+  uint32_t flags;         /* reserved, must be 0 */
   /* HOST pointers to fp32[T] tables, copied at create.  Built by the caller with the reference's own
    * expressions so they are bit-equal to it: util.py:111-123 and diffwave_sde.py:57-58.          */
   const float* alpha;

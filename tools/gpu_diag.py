@@ -42,7 +42,7 @@ def _small():
     import audiopure_b200 as ap
     from oracle import weights as W
     cfg = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
-    m = ap.WaveNet_Speech_Commands(**cfg, single_cta=bool(os.environ.get("AP_SINGLE")))
+    m = ap.WaveNet_Speech_Commands(**cfg)
     m.load_state_dict(W.make_state_dict(99, cfg))
     return m.cuda().eval(), cfg
 
@@ -81,7 +81,7 @@ def stage_full():
     import torch
     import audiopure_b200 as ap
     from oracle import weights as W
-    m = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG, single_cta=bool(os.environ.get("AP_SINGLE")))
+    m = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
     m.load_state_dict(W.make_state_dict(1234))
     m = m.cuda().eval()
     g = np.load(os.path.join(ROOT, "tests/golden/wavenet_full.npz"))
@@ -97,7 +97,7 @@ def stage_purify():
     import torch
     import audiopure_b200 as ap
     from oracle import weights as W
-    m = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG, single_cta=bool(os.environ.get("AP_SINGLE")))
+    m = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
     m.load_state_dict(W.make_state_dict(1234))
     m = m.cuda().eval()
     hp = ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
@@ -128,7 +128,7 @@ def stage_b64():
     import torch
     import audiopure_b200 as ap
     from oracle import weights as W
-    m = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG, single_cta=bool(os.environ.get("AP_SINGLE")))
+    m = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
     m.load_state_dict(W.make_state_dict(1234))
     m = m.cuda().eval()
     x = W.make_waveforms(64, 16000, seed=2).cuda()

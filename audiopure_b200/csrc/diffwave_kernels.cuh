@@ -26,6 +26,7 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr float kSqrtHalf = 0.70710678118654752440f;
+constexpr int kTailPrefetch = 16;  // K steps of gate tiles kept in flight into L2 by the tail kernel
 
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -171,7 +172,7 @@ struct LayerArgs {
   int L, tiles_per_clip, num_tiles;
   int dilation, layer;
   int write_h;  // 0 for the last layer (its residual output is never consumed)
-  int debug;    // experiment switches (AP_DEBUG env): 2 no MUFU, 4 no h stores, 8 no gate store
+  int debug;    // experiment switches (AP_DEBUG env): 2 no MUFU, 4 no h stores, 8 no gate store, 16 no L2 prefetch
 };
 struct LayerBias {  // passed by value: lives in the constant bank, read with warp-uniform indices
   float b1[512];    // conv bias, permuted like W1's rows
@@ -241,6 +242,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     uint32_t it = 0;
     for (int u = unit0; 2 * u < a.num_tiles; u += units) {
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
+      // The rows a tile touches first come from DRAM (the previous layer wrote 0.5 GB since), and a DRAM miss is
+      // longer than the ring can cover: pull the NEXT tile's three tap windows into L2 one tile-time ahead.
+      if (2 * (u + units) < a.num_tiles && !(a.debug & 16) && elect_one()) {
+        const TileCoord tn = tile_coord(2 * (u + units) + rank, a.num_tiles, a.tiles_per_clip);
+        if (tn.valid) {
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+            for (int cq = 0; cq < 4; ++cq) tma_prefetch_3d(&tm_h, cq * 64, tn.l0 + (tap - 1) * a.dilation, tn.b);
+        }
+      }
+      __syncwarp();
       for (int c = 0; c < 2; ++c) {
         for (int ks = 0; ks < 12; ++ks, ++it) {
           const int s = it % T::kStages;
@@ -569,11 +582,19 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
     };
     for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
+      const bool has_next = 2 * (u + units) < a.num_tiles;
+      const TileCoord tn = tile_coord(2 * (u + units) + rank, a.num_tiles, a.tiles_per_clip);
       for (int ks = 0; ks < total_ks; ++ks, ++it) {
         if (ks == J && i > 0) load_wf();
         const int s = it % T::kStages;
         mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 12);
         if (elect_one()) {
+          // every gate tile is a compulsory DRAM read: keep kPrefetch K steps in flight into L2 (the ring alone
+          // holds 64 KB per SM, far below bandwidth x latency)
+          const int kp = ks + kTailPrefetch;
+          if (kp < total_ks) tma_prefetch_4d(&tm_gate, (kp & 3) * 64, tc.l0, tc.b, kp >> 2);
+          else if (has_next && tn.valid && kp - total_ks < total_ks)
+            tma_prefetch_4d(&tm_gate, ((kp - total_ks) & 3) * 64, tn.l0, tn.b, (kp - total_ks) >> 2);
           mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
           uint8_t* sa = stage_base + s * T::kStageBytes;
           tma_load_4d_pair(sa, &tm_gate, full0 + 8 * s, (ks & 3) * 64, tc.l0, tc.b, ks >> 2);

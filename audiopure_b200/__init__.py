@@ -16,7 +16,7 @@ All compute on the path runs in hand-written CUDA kernels behind the C ABI of in
 
 from .acoustic_system import AcousticSystem  # noqa: F401
 from .certified_robust import RobustCertificate  # noqa: F401
-from .classifier import CifarResNeXt  # noqa: F401
+from .classifier import CifarResNeXt, FusedResNeXt  # noqa: F401
 from .diffwave_ddpm import DiffWave, create_diffwave_model  # noqa: F401
 from .diffwave_sde import RevDiffWave, RevVPSDE  # noqa: F401
 from .schedule import calc_diffusion_hyperparams, calc_diffusion_step_embedding  # noqa: F401

@@ -6,11 +6,12 @@ purify -> log-mel -> classify step without the reference checkout.  Same layer n
 ``audio_models/ConvNets_SpeechCommands/models/resnext.py`` so its checkpoints' state dicts load.
 """
 
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn import init
 
-__all__ = ["CifarResNeXt"]
+__all__ = ["CifarResNeXt", "FusedResNeXt"]
 
 
 class ResNeXtBottleneck(nn.Module):
@@ -77,3 +78,58 @@ class CifarResNeXt(nn.Module):
         x = self.stage_3(self.stage_2(self.stage_1(x)))
         x = F.avg_pool2d(x, 8, 1)
         return self.classifier(x.view(-1, self.stages[3]))
+
+
+class _FusedBottleneck(nn.Module):
+    def __init__(self, src: ResNeXtBottleneck):
+        super().__init__()
+        self.reduce = _fold(src.conv_reduce, src.bn_reduce)
+        self.conv = _fold(src.conv_conv, src.bn)
+        self.expand = _fold(src.conv_expand, src.bn_expand)
+        self.shortcut = None
+        if len(src.shortcut) > 0:
+            self.shortcut = _fold(src.shortcut.shortcut_conv, src.shortcut.shortcut_bn)
+
+    def forward(self, x):
+        y = F.relu(self.reduce(x), inplace=True)
+        y = F.relu(self.conv(y), inplace=True)
+        y = self.expand(y)
+        r = x if self.shortcut is None else self.shortcut(x)
+        return F.relu(r + y, inplace=True)
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
+    """conv (no bias) + eval-mode batch-norm -> one conv with bias (exact in real arithmetic)."""
+    out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
+                    groups=conv.groups, bias=True)
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    out.weight.data.copy_(conv.weight.detach() * scale.reshape(-1, 1, 1, 1))
+    out.bias.data.copy_(bn.bias.detach() - bn.running_mean.detach() * scale)
+    return out
+
+
+class FusedResNeXt(nn.Module):
+    """Inference form of a trained/loaded ``CifarResNeXt``: batch-norms folded into the
+    convolutions, channels-last, bf16 weights and activations with fp32 accumulation (cuDNN), fp32 logits.
+    ``FusedResNeXt(clf)`` is a drop-in for ``clf.eval()`` in the ``classifier`` slot; it removes the 31 batch-norm
+    and ~50 layout-conversion launches per batch that the reference module issues."""
+
+    def __init__(self, src: CifarResNeXt, dtype=torch.bfloat16):
+        super().__init__()
+        assert not src.training, "fold batch-norm statistics of an eval() module"
+        self.dtype = dtype
+        self.stem = _fold(src.conv_1_3x3, src.bn_1)
+        self.blocks = nn.Sequential(*[_FusedBottleneck(b) for stage in (src.stage_1, src.stage_2, src.stage_3) for b in stage])
+        self.classifier = src.classifier
+        self.width = src.stages[3]
+        self.to(memory_format=torch.channels_last)
+        self.stem.to(dtype)
+        self.blocks.to(dtype)
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        x = F.relu(self.stem(x), inplace=True)
+        x = self.blocks(x)
+        x = F.avg_pool2d(x, 8, 1).float()
+        return self.classifier(x.reshape(-1, self.width))

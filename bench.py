@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--t-star", type=int, default=T_STAR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clips", type=int, default=1)
+    ap.add_argument("--classifier", default="fused", choices=["fused", "module"],
+                    help="consumer ResNeXt-29: bf16 channels-last with folded batch-norm, or the plain fp32 nn.Module")
     return ap.parse_args()
 
 
@@ -163,6 +165,7 @@ def workload_config(args):
                     "1-s 16 kHz clips per GPU, DiffWave-unconditional (36 layers, 256 ch, T=200), random-init weights"
                     % (args.t_star, args.batch),
         "batch_per_gpu": args.batch, "t_star": args.t_star, "clip_samples": CLIP_LEN,
+        "classifier": "ResNeXt-29 8x64 consumer (cuDNN): " + ("bf16 channels-last, batch-norm folded" if args.classifier == "fused" else "fp32 nn.Module"),
         "l2": "no flush needed: every step streams a ~20 GB activation workspace, far larger than the 126 MB L2",
     }
 
@@ -180,6 +183,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True  # as the reference's eval scripts do (adaptive_attack_eval.py:69)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -191,6 +195,8 @@ def run_ours(args):
     clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
     clf.load_state_dict(o_resnext.make_state_dict(4321))
     clf = clf.to(dev).eval()
+    if args.classifier == "fused":
+        clf = ap.FusedResNeXt(clf).to(dev)
     system = ap.AcousticSystem(classifier=clf, transform=ap.LogMelSpectrogram().to(dev), defender=defender)
     eng = model.engine()
 

@@ -317,6 +317,19 @@ def test_acoustic_system_vs_reference(full_model, hp, classifier, golden):
         ap.AcousticSystem(classifier, None, dw, defense_type="other")
 
 
+def test_fused_bf16_classifier_agrees_with_fp32(classifier):
+    """North star: classifier top-1 agreement >= 99.5 % on synthetic clips (bf16 fused consumer vs fp32 module)."""
+    fused = ap.FusedResNeXt(classifier).cuda()
+    tr = ap.LogMelSpectrogram().cuda()
+    x = W.make_waveforms(512, 16000, seed=12).cuda()
+    with torch.no_grad():
+        spec = tr(x)
+        a, b = classifier(spec), fused(spec)
+    agree = float((a.argmax(1) == b.argmax(1)).float().mean())
+    assert agree >= 0.995, agree
+    assert rel_l2(b, a) < 5e-2
+
+
 def test_vote_counts_kernel_bit_exact():
     lib = _lib.load()
     g = torch.Generator().manual_seed(0)

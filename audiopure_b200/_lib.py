@@ -95,7 +95,8 @@ class AudioPureError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB
+    """In-tree library; AP_LIB=/path/to/variant.so selects an alternative build (A/B experiments only)."""
+    return os.environ.get("AP_LIB") or _build.LIB
 
 
 def load():

@@ -26,7 +26,6 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr float kSqrtHalf = 0.70710678118654752440f;
-constexpr int kTailPrefetch = 16;  // K steps of gate tiles kept in flight into L2 by the tail kernel
 
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -114,16 +113,20 @@ __global__ void __launch_bounds__(256) prologue_kernel(const float* __restrict__
 // 0.87 ms per layer launch at B = 64 before the epilogue rework).
 // ---------------------------------------------------------------------------------------------------
 struct Tc {
-  static constexpr int kStages = 4;                 // TMA -> MMA ring depth
   static constexpr uint32_t kBRows = 128;           // weight rows staged per CTA per K step (half of N = 256)
   static constexpr uint32_t kBBytes = kBRows * 128;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kRing = kStages * kStageBytes;
   static constexpr uint32_t kEpiWarps = kEpiThreads / 32;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(256, 256);
-  static constexpr uint32_t kXSlotBytes = kABytes;  // one [128 x 64] chunk of the layer input (residual term)
-  static constexpr uint32_t kLayerSmem = kRing + kTileBytes + 2 * kXSlotBytes + 32 * 8 + 1024;
-  static constexpr uint32_t kTailSmem = kRing + kTileBytes + 3 * 256 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 1024;
+  // TMA -> MMA ring depth.  The ring is latency-sensitive (3 -> 4 stages: -7 % layer, -11 % tail time), so
+  // everything else in shared memory is squeezed into ONE 64 KB operand tile per kernel to afford 5 stages.
+#ifndef AP_LAYER_STAGES
+#define AP_LAYER_STAGES 5
+#endif
+  static constexpr int kLayerStages = AP_LAYER_STAGES;
+  static constexpr int kTailStages = 4;
+  static constexpr uint32_t kLayerSmem = kLayerStages * kStageBytes + kTileBytes + 32 * 8 + 1024;
+  static constexpr uint32_t kTailSmem = kTailStages * kStageBytes + kTileBytes + 3 * 256 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 1024;
 };
 
 // Work distribution shared by all warp roles: unit u covers tiles 2u and 2u+1; this CTA takes tile 2u + rank.
@@ -162,17 +165,18 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_tiles, int til
 // D2 -> bufA again (its gate half was drained by then), with (bufA, bufB) = (X, Y) for even tiles and
 // (Y, X) for odd tiles, so the MMA warp runs ahead of the epilogue by one chunk at all times.
 //
-// Epilogue data movement is all TMA: the residual input x arrives in two 16 KB slots (loaded by warp 2),
-// the gate tile and h_next leave by TMA stores.  Every epilogue warp (q, hh) owns rows [32q, 32q+32) of the
-// 64-channel sub-tiles {hh, 2+hh} of the 64 KB operand tile for BOTH uses (gate, then h_next staging), and
-// stores its own [32 x 64] boxes, so the eight warps never need a CTA-wide barrier.  (Per-thread 16-byte
-// global accesses at a 512-byte stride cost 0.91 -> 0.56 ms per launch in an ablation; see DESIGN.md.)
+// Epilogue data movement is all TMA and everything lives in the ONE 64 KB operand tile: the epilogue writes the
+// gate there (GEMM2's A operand, also TMA-stored to HBM); once GEMM2 has consumed it, warp 2 TMA-loads the
+// layer input x over it (residual term), the epilogue turns x into h_next IN PLACE and TMA-stores it.  Every
+// epilogue warp (q, hh) owns rows [32q, 32q+32) of the 64-channel sub-tiles {hh, 2+hh} for all three uses
+// and stores its own [32 x 64] boxes, so the eight warps never need a CTA-wide barrier.  (Per-thread 16-byte
+// global accesses at a 512-byte stride cost 0.91 -> 0.56 ms per launch in an ablation; see profiles/.)
 // ---------------------------------------------------------------------------------------------------
 struct LayerArgs {
   int L, tiles_per_clip, num_tiles;
   int dilation, layer;
   int write_h;  // 0 for the last layer (its residual output is never consumed)
-  int debug;    // experiment switches (AP_DEBUG env): 2 no MUFU, 4 no h stores, 8 no gate store, 16 no L2 prefetch
+  int debug;    // ablation switches (AP_DEBUG env, profiles/r01_ablation.md): 2 no MUFU, 4 no h_next store, 8 no gate store
 };
 struct LayerBias {  // passed by value: lives in the constant bank, read with warp-uniform indices
   float b1[512];    // conv bias, permuted like W1's rows
@@ -188,18 +192,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
-  uint8_t* gate_s = smem + T::kRing;                 // gate tile, later h_next staging
-  uint8_t* x_s = gate_s + kTileBytes;                // 2 x [128 x 64] slots of the layer input
-  uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + 2 * T::kXSlotBytes);
+  constexpr int kStages = T::kLayerStages;
+  uint8_t* gate_s = smem + kStages * T::kStageBytes;  // the operand tile: gate, then x, then h_next
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gate_s + kTileBytes);
   uint64_t* full = bars;             // [kStages] TMA -> MMA            (leader's copy is the live one)
-  uint64_t* empty = bars + 4;        // [kStages] MMA -> TMA            (per CTA, multicast commit)
-  uint64_t* d1_full = bars + 8;      // [2] chunk accumulator ready     MMA -> epilogue (per CTA)
-  uint64_t* gate_ready = bars + 10;  // [2] gate half in smem, chunk's TMEM drained   epilogue -> MMA (leader)
-  uint64_t* d2_full = bars + 12;     //     residual accumulator ready  MMA -> epilogue (per CTA)
-  uint64_t* d2_empty = bars + 13;    //     residual accumulator drained epilogue -> MMA (leader)
-  uint64_t* x_full = bars + 14;      // [2] x slot loaded               x producer -> epilogue
-  uint64_t* x_empty = bars + 16;     // [2] x slot consumed             epilogue -> x producer
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* empty = bars + 6;        // [kStages] MMA -> TMA            (per CTA, multicast commit)
+  uint64_t* d1_full = bars + 12;     // [2] chunk accumulator ready     MMA -> epilogue (per CTA)
+  uint64_t* gate_ready = bars + 14;  // [2] gate half in smem, chunk's TMEM drained   epilogue -> MMA (leader)
+  uint64_t* d2_full = bars + 16;     //     residual accumulator ready  MMA -> epilogue (per CTA)
+  uint64_t* d2_empty = bars + 17;    //     residual accumulator drained epilogue -> MMA (leader)
+  uint64_t* tile_free = bars + 18;   //     gate tile dead (GEMM2 + gate stores done)  epilogue -> x producer
+  uint64_t* x_full = bars + 19;      // [4] x sub-tile k landed in the operand tile    x producer -> epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -207,18 +211,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   const int units = static_cast<int>(gridDim.x >> 1);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < T::kStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 2);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&d1_full[s], 1);
       mbar_init(&gate_ready[s], 2 * T::kEpiWarps);
-      mbar_init(&x_full[s], 1);
-      mbar_init(&x_empty[s], T::kEpiWarps / 2);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&x_full[s], 1);
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, 2 * T::kEpiWarps);
+    mbar_init(tile_free, T::kEpiWarps);
     fence_mbar_init();
     tma_prefetch_desc(&tm_h);
     tma_prefetch_desc(&tm_w1);
@@ -242,22 +246,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     uint32_t it = 0;
     for (int u = unit0; 2 * u < a.num_tiles; u += units) {
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
-      // The rows a tile touches first come from DRAM (the previous layer wrote 0.5 GB since), and a DRAM miss is
-      // longer than the ring can cover: pull the NEXT tile's three tap windows into L2 one tile-time ahead.
-      if (2 * (u + units) < a.num_tiles && !(a.debug & 16) && elect_one()) {
-        const TileCoord tn = tile_coord(2 * (u + units) + rank, a.num_tiles, a.tiles_per_clip);
-        if (tn.valid) {
-#pragma unroll
-          for (int tap = 0; tap < 3; ++tap)
-#pragma unroll
-            for (int cq = 0; cq < 4; ++cq) tma_prefetch_3d(&tm_h, cq * 64, tn.l0 + (tap - 1) * a.dilation, tn.b);
-        }
-      }
-      __syncwarp();
       for (int c = 0; c < 2; ++c) {
         for (int ks = 0; ks < 12; ++ks, ++it) {
-          const int s = it % T::kStages;
-          mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 1);
+          const int s = it % kStages;
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 1);
           if (elect_one()) {
             mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
             uint8_t* sa = stage_base + s * T::kStageBytes;
@@ -269,8 +261,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         }
       }
       for (int ks = 0; ks < 4; ++ks, ++it) {
-        const int s = it % T::kStages;
-        mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 2);
+        const int s = it % kStages;
+        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 2);
         if (elect_one()) {
           mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kBBytes);
           tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_w2, full0 + 8 * s, ks * 64,
@@ -296,8 +288,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
           }
           const uint32_t d = c ? bufB : bufA;
           for (int ks = 0; ks < 12; ++ks, ++it) {
-            const int s = it % T::kStages;
-            mbar_wait(&full[s], (it / T::kStages) & 1, 4);
+            const int s = it % kStages;
+            mbar_wait(&full[s], (it / kStages) & 1, 4);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
@@ -315,8 +307,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
             mbar_wait(&gate_ready[ks >> 1], p, 5);
             tc_fence_after();
           }
-          const int s = it % T::kStages;
-          mbar_wait(&full[s], (it / T::kStages) & 1, 6);
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1, 6);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = gdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
@@ -332,20 +324,20 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     }
   } else if (warp == 2) {
     // ======================= x producer: the layer input again, for the residual term ==================
-    // chunk k (channels [64k, 64k+64)) goes to slot k & 1; warpgroup hh of the epilogue consumes slot hh.
+    // Once the epilogue reports the gate tile dead (GEMM2 and the gate stores have read it), load the tile's
+    // own 128 input rows over it, one barrier per 64-channel sub-tile.
     int i = 0;
     for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
-      for (int kk = 0; kk < 2; ++kk) {
-        for (int sl = 0; sl < 2; ++sl) {
-          mbar_wait(&x_empty[sl], ((2 * i + kk) & 1) ^ 1, 9);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&x_full[sl], T::kXSlotBytes);
-            tma_load_3d(x_s + sl * T::kXSlotBytes, &tm_h, &x_full[sl], (sl + 2 * kk) * 64, tc.l0, tc.b);
-          }
-          __syncwarp();
+      mbar_wait(tile_free, i & 1, 9);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mbar_arrive_expect_tx(&x_full[k], kABytes);
+          tma_load_3d(gate_s + k * kABytes, &tm_h, &x_full[k], k * 64, tc.l0, tc.b);
         }
       }
+      __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
     // ======================= epilogue (8 warps, each owns rows [32q,+32) of sub-tiles {hh, 2+hh}) ========
@@ -417,25 +409,29 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         }
       }
 
-      // ---- residual output: h_next = sqrt(.5) x + D2 + c2, staged in this warp's regions of the tile ----
+      // ---- residual output: h_next = sqrt(.5) x + D2 + c2, computed in place over x in the operand tile ----
       mbar_wait(d2_full, p, 8);  // also: the MMAs have finished reading the gate tile
       tc_fence_after();
-      if (lane == 0) tma_store_wait_read();  // ... and so have this warp's gate stores
+      if (lane == 0) {
+        tma_store_wait_read();   // ... and so have this warp's gate stores: the tile may be overwritten with x
+        mbar_arrive(tile_free);
+      }
       __syncwarp();
 #pragma unroll 1
       for (int kk = 0; kk < 2; ++kk) {
         const int k = hh + 2 * kk;  // 64-channel chunk == sub-tile index
-        mbar_wait(&x_full[hh], (2 * i + kk) & 1, 10);
-        const uint8_t* xs = x_s + hh * T::kXSlotBytes;
         uint8_t* sub = gate_s + k * kABytes;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(bufA + lane_addr + k * 64, r0);
+        tmem_ld32(bufA + lane_addr + k * 64 + 32, r1);
+        mbar_wait(&x_full[k], p, 10);
+        tmem_ld_wait();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(bufA + lane_addr + k * 64 + half * 32, r);
+          const uint32_t* r = half ? r1 : r0;
           uint4 xv[4];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) xv[v] = *reinterpret_cast<const uint4*>(xs + sw128_offset(row, half * 4 + v));
-          tmem_ld_wait();
+          for (int v = 0; v < 4; ++v) xv[v] = *reinterpret_cast<const uint4*>(sub + sw128_offset(row, half * 4 + v));
           const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
           const float* cc = bias.c2 + k * 64 + half * 32;
           uint4 ov[4];
@@ -449,20 +445,19 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
 #pragma unroll
           for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(sub + sw128_offset(row, half * 4 + v)) = ov[v];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&x_empty[hh]);
+        if (kk == 1) {  // all of this warp's accumulator columns are in registers / consumed
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(d2_empty_l);
+        }
       }
-      tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(d2_empty_l);
-        if (a.write_h && !(a.debug & 4)) {
+      if (lane == 0 && a.write_h && !(a.debug & 4)) {
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
-            tma_store_3d(&tm_h_st, gate_s + (hh + 2 * kk) * kABytes + q * 32 * 128, (hh + 2 * kk) * 64, l0 + q * 32, b);
-          tma_store_commit();
-        }
+        for (int kk = 0; kk < 2; ++kk)
+          tma_store_3d(&tm_h_st, gate_s + (hh + 2 * kk) * kABytes + q * 32 * 128, (hh + 2 * kk) * 64, l0 + q * 32, b);
+        tma_store_commit();
       }
     }
     if (lane == 0) tma_store_wait_all();
@@ -512,7 +507,8 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
-  uint8_t* s_tile = smem + T::kRing;
+  constexpr int kStages = T::kTailStages;
+  uint8_t* s_tile = smem + kStages * T::kStageBytes;
   float* bss = reinterpret_cast<float*>(s_tile + kTileBytes);
   float* bfs = bss + 256;
   float* wos = bfs + 256;
@@ -537,7 +533,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
     wos[i] = a.wo[i];
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < T::kStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 2);
       mbar_init(&empty[s], 1);
     }
@@ -571,8 +567,8 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
     int i = 0;
     auto load_wf = [&]() {
       for (int ks = 0; ks < 4; ++ks, ++it) {
-        const int s = it % T::kStages;
-        mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 11);
+        const int s = it % kStages;
+        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 11);
         if (elect_one()) {
           mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kBBytes);
           tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_wf, full0 + 8 * s, ks * 64, brow);
@@ -582,19 +578,11 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
     };
     for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
-      const bool has_next = 2 * (u + units) < a.num_tiles;
-      const TileCoord tn = tile_coord(2 * (u + units) + rank, a.num_tiles, a.tiles_per_clip);
       for (int ks = 0; ks < total_ks; ++ks, ++it) {
         if (ks == J && i > 0) load_wf();
-        const int s = it % T::kStages;
-        mbar_wait(&empty[s], ((it / T::kStages) & 1) ^ 1, 12);
+        const int s = it % kStages;
+        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 12);
         if (elect_one()) {
-          // every gate tile is a compulsory DRAM read: keep kPrefetch K steps in flight into L2 (the ring alone
-          // holds 64 KB per SM, far below bandwidth x latency)
-          const int kp = ks + kTailPrefetch;
-          if (kp < total_ks) tma_prefetch_4d(&tm_gate, (kp & 3) * 64, tc.l0, tc.b, kp >> 2);
-          else if (has_next && tn.valid && kp - total_ks < total_ks)
-            tma_prefetch_4d(&tm_gate, ((kp - total_ks) & 3) * 64, tn.l0, tn.b, (kp - total_ks) >> 2);
           mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
           uint8_t* sa = stage_base + s * T::kStageBytes;
           tma_load_4d_pair(sa, &tm_gate, full0 + 8 * s, (ks & 3) * 64, tc.l0, tc.b, ks >> 2);
@@ -615,8 +603,8 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         mbar_wait(s_ready, ip & 1, 13);
         tc_fence_after();
         for (int ks = 0; ks < 4; ++ks, ++it) {
-          const int s = it % T::kStages;
-          mbar_wait(&full[s], (it / T::kStages) & 1, 14);
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1, 14);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = sdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
@@ -638,8 +626,8 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         }
         for (int ks = 0; ks < total_ks; ++ks, ++it) {
           if (ks == J && i > 0) head_gemm(i - 1);
-          const int s = it % T::kStages;
-          mbar_wait(&full[s], (it / T::kStages) & 1, 16);
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1, 16);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);

@@ -71,6 +71,26 @@ class RevVPSDE(torch.nn.Module):
         return torch.full_like(x, scale * beta_t ** 0.5)
 
 
+class _PurifyWithLinearisedGrad(torch.autograd.Function):
+    """Forward: the CUDA purifier.  Backward: the Jacobian the reference's ``sdeint_adjoint`` sees.
+
+    ``RevVPSDE.f`` evaluates the network through ``DiffWave.compute_eps_t``, which is ``@torch.no_grad()``
+    (diffwave_ddpm.py:166), so the only term of the drift that carries gradient is ``0.5 * beta_t * x``
+    (diffwave_sde.py:79,104,118-125), the diffusion ``g`` does not depend on x, and the initial diffusion is the
+    scaling ``sqrt(abar_{t-1})`` (:190-191).  The input-Jacobian of one Euler-Maruyama purification is therefore
+    the scalar ``sqrt(abar_{t-1}) * prod_k (1 + beta_k / 2)`` times the identity (SURVEY.md section 8f-1);
+    supplying it here also spares the adjoint pass its second set of t network evaluations."""
+
+    @staticmethod
+    def forward(ctx, x, engine, t, z, seed, clip_offset, scale):
+        ctx.scale = scale
+        return engine.sde_purify(x, t, z=z, seed=seed, clip_offset=clip_offset)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return grad_out * ctx.scale, None, None, None, None, None, None
+
+
 class RevDiffWave(torch.nn.Module):
     """diffwave_sde.py:138-218.  ``args`` carries the reference's attribute names: ``ddpm_path``, ``ddpm_config``,
     ``t``, ``sample_step``, ``rand_t``, ``t_delta``, ``use_bm``, ``score_type``.  A ready ``DiffWave`` may be
@@ -110,10 +130,20 @@ class RevDiffWave(torch.nn.Module):
                 total_noise_levels = self.args.t + np.random.randint(-self.args.t_delta, self.args.t_delta)
             self._calls += 1
             seed = (self.seed * 0x9E3779B97F4A7C15 + 0x5DE00000 + self._calls) & 0xFFFFFFFFFFFFFFFF
-            x0 = eng.sde_purify(x0, total_noise_levels, z=None if z is None else z[it], seed=seed,
-                                clip_offset=clip_offset)
+            zi = None if z is None else z[it]
+            if torch.is_grad_enabled() and x0.requires_grad:  # adaptive attack (white_box_attack.py:437-439)
+                x0 = _PurifyWithLinearisedGrad.apply(x0, eng, total_noise_levels, zi, seed, clip_offset,
+                                                     self.input_jacobian(total_noise_levels))
+            else:
+                x0 = eng.sde_purify(x0, total_noise_levels, z=zi, seed=seed, clip_offset=clip_offset)
             xs.append(x0)
         return torch.cat(xs, dim=0)
+
+    def input_jacobian(self, t):
+        """d(purified)/d(input) as a scalar: sqrt(abar_{t-1}) * prod_{k<t} (1 + beta_k / 2)."""
+        b = self.rev_vpsde.discrete_betas.double()
+        ac = self.rev_vpsde.alphas_cumprod.double()
+        return float(ac[t - 1].sqrt() * torch.prod(1.0 + 0.5 * b[:t]))
 
     def forward(self, x, z: torch.Tensor = None):
         return self.audio_editing_sample(x, z=z)

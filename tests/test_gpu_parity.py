@@ -240,6 +240,34 @@ def test_sde_sample_step_concatenates(small_model, hp):
     assert out.shape == (6, 1, 512)  # diffwave_sde.py:212
 
 
+def test_sde_linearised_gradient_matches_oracle_autograd(small_model, hp):
+    """with eps under no_grad the purifier's input-Jacobian is a scalar; check it against autograd
+    through the oracle's Euler-Maruyama restatement (eps detached, as compute_eps_t does)."""
+    sd = W.make_state_dict(99, SMALL)
+    tab = o_schedule.sde_tables()
+    t = 3
+    x = W.make_waveforms(1, 2048, seed=6)
+    z = W.make_noise((t + 1, 1, 1, 2048), seed=23)
+    xo = x.clone().requires_grad_(True)
+    eps_fn = lambda xx, k: o_wavenet.eps_theta(sd, xx.detach(), k, SMALL)  # noqa: E731
+    yo = o_purify.sde_purify(tab, eps_fn, xo, t, z[0], z[1:].reshape(t, 1, 2048))
+    w = W.make_noise((1, 1, 2048), seed=24)
+    (yo * w).sum().backward()
+
+    class Args:
+        pass
+
+    args = Args()
+    args.t, args.sample_step, args.rand_t, args.t_delta, args.use_bm, args.score_type = t, 1, False, 0, False, "guided_diffusion"
+    rev = ap.RevDiffWave(args, model=ap.DiffWave(small_model, hp, reverse_timestep=t))
+    xg = x.cuda().requires_grad_(True)
+    yg = rev(xg, z=z[None])
+    (yg * w.cuda()).sum().backward()
+    assert rel_l2(yg, yo) < WAVE_GATE
+    assert rel_l2(xg.grad, xo.grad) < 1e-4
+    assert abs(rev.input_jacobian(t) - float((xo.grad / w).mean())) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------ philox noise --
 def test_philox_noise_is_shard_invariant_and_seeded(small_model, hp):
     dw = ap.DiffWave(small_model, hp, reverse_timestep=3, seed=5)
@@ -382,6 +410,28 @@ def test_sharded_counts_equal_single_rank(small_model, hp, classifier):
         parts.append(rc.smooth_predict(x, 37, 0.25, batch_size=hi - lo))
     assert int(whole.sum()) == 37
     assert torch.equal(parts[0] + parts[1], whole)
+
+
+def test_factory_reads_reference_config_and_checkpoint(tmp_path):
+    """create_diffwave_model (diffwave_ddpm.py:395-411): same config.json keys, same {'model_state_dict': ...} .pkl,
+    and a KWS-style non-16000 clip length (kws_adaptive_attack_eval.py:178)."""
+    cfgp, ckpt = tmp_path / "config.json", tmp_path / "1000.pkl"
+    cfgp.write_text(json.dumps({"diffusion_config": W.DEFAULT_DIFFUSION_CONFIG, "wavenet_config": SMALL,
+                                "train_config": {}, "dist_config": {}}))
+    sd = W.make_state_dict(99, SMALL)
+    torch.save({"model_state_dict": sd, "optimizer_state_dict": {}}, ckpt)
+    dw = ap.create_diffwave_model(str(ckpt), str(cfgp), reverse_timestep=2)
+    assert dw.reverse_timestep == 2 and dw.diffusion_hyperparams["T"] == 200
+    x = W.make_waveforms(2, 12800, seed=3)
+    got = dw.compute_eps_t(x.cuda(), 5)
+    assert rel_l2(got, o_wavenet.eps_theta(sd, x, 5, SMALL)) < EPS_GATE
+    args = type("A", (), dict(ddpm_path=str(ckpt), ddpm_config=str(cfgp), t=2, sample_step=1, rand_t=False, t_delta=0,
+                              use_bm=False, score_type="guided_diffusion"))()
+    rev = ap.RevDiffWave(args)
+    rev.rev_vpsde.audio_shape = (1, 12800)
+    assert rev(x.cuda()).shape == (2, 1, 12800)
+    with pytest.raises(NotImplementedError):
+        ap.RevVPSDE(dw, score_type="score_sde")
 
 
 # ---------------------------------------------------------------------------------------- error behaviour --

@@ -146,7 +146,7 @@ struct WsLayout {
 
 WsLayout ws_layout(const ap_net* n, int Bc, int L) {
   WsLayout w;
-  w.h_bytes = align_up(static_cast<size_t>(Bc) * L * ap::kC * 2, 1024);
+  w.h_bytes = static_cast<size_t>(Bc) * L * ap::kC * 2;  // a multiple of 512: enough for TMA (16 B) and 128 B lines
   w.off_h[0] = 0;
   w.off_h[1] = w.h_bytes;
   w.off_gate = 2 * w.h_bytes;
@@ -166,9 +166,6 @@ int ensure_maps(ap_net* n, uint8_t* ws, int Bc, int L) {
       return 1;
   const uint64_t d4[4] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc),
                           static_cast<uint64_t>(n->layers)};
-  // gate[layer] slabs are h_bytes apart; h_bytes == Bc*L*512 whenever that is a multiple of 1024
-  if (w.h_bytes != static_cast<size_t>(Bc) * L * ap::kC * 2)
-    return fail("internal: B*L must be even so that layer slabs are contiguous");
   if (make_map(&n->tm_gate, ws + w.off_gate, 4, d4, ap::kTileT) || make_map(&n->tm_gate_st, ws + w.off_gate, 4, d4, 32))
     return 1;
   n->cached_ws = ws;
@@ -262,7 +259,6 @@ int launch_axpbz(const float* x, const float* z, float* y, float ca, float cb, l
 int check_call(const ap_net* n, int B, int L, const void* ws, size_t ws_bytes) {
   AP_CHECK(n, "null handle");
   AP_CHECK(B > 0 && L > 0, "B and L must be positive");
-  AP_CHECK(L % 2 == 0, "L must be even");
   AP_CHECK(ws, "null workspace");
   AP_CHECK(reinterpret_cast<uintptr_t>(ws) % 1024 == 0, "workspace must be 1024-byte aligned");
   AP_CHECK(ws_bytes >= ap_workspace_bytes(n, B, L), "workspace too small: see ap_workspace_bytes");

@@ -148,6 +148,15 @@ def test_eps_is_batch_invariant_at_full_batch(full_model):
     assert torch.isfinite(big).all()
 
 
+def test_eps_odd_length_and_tiny_clip(small_model):
+    """Ragged shapes: odd L (tile of 1 valid row at the end), L below one tile, single-clip pair with a dummy tile."""
+    sd = W.make_state_dict(99, SMALL)
+    for B, L in ((1, 129), (3, 77), (1, 128)):
+        x = W.make_waveforms(B, L, seed=L)
+        got = small_model.engine().eps(x.cuda(), 4)
+        assert rel_l2(got, o_wavenet.eps_theta(sd, x, 4, SMALL)) < EPS_GATE, (B, L)
+
+
 def test_eps_chunking_over_max_chunk():
     m = ap.WaveNet_Speech_Commands(**SMALL, max_chunk=2)
     m.load_state_dict(W.make_state_dict(99, SMALL))

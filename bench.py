@@ -176,7 +176,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import audiopure_b200 as ap
-    from oracle import resnext as o_resnext, weights as W  # seeded random-init checkpoints only (no compute)
+    from audiopure_b200 import synthetic as S
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,13 +187,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    model = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
-    model.load_state_dict(W.make_state_dict(1234))
+    model = ap.WaveNet_Speech_Commands(**S.DEFAULT_WAVENET_CONFIG)
+    model.load_state_dict(S.diffwave_state_dict(1234))
     model = model.to(dev).eval()
-    hp = ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    hp = ap.calc_diffusion_hyperparams(**S.DEFAULT_DIFFUSION_CONFIG)
     defender = ap.DiffWave(model, hp, reverse_timestep=args.t_star, seed=rank)
     clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
-    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    clf.load_state_dict(S.resnext_state_dict(4321))
     clf = clf.to(dev).eval()
     if args.classifier == "fused":
         clf = ap.FusedResNeXt(clf).to(dev)
@@ -201,7 +201,7 @@ def run_ours(args):
     eng = model.engine()
 
     B = args.batch
-    x_host = W.make_waveforms(B, CLIP_LEN, seed=rank).pin_memory()
+    x_host = S.waveforms(B, CLIP_LEN, seed=rank).pin_memory()
     x_dev = x_host.to(dev)
 
     def step_resident():

@@ -75,3 +75,17 @@ def test_packing_is_refreshed_after_load_state_dict():
     m._engine = object()
     m.load_state_dict(W.make_state_dict(99, SMALL))
     assert m._engine is None
+
+
+def test_product_synthetic_checkpoints_equal_oracle_ones():
+    """audiopure_b200.synthetic (used by bench.py / tools) and oracle.weights (used by tests and fixtures) must
+    generate the same tensors, so benchmark numbers are on the weights the parity tests cover."""
+    from audiopure_b200 import synthetic as S
+    from oracle import resnext as o_resnext
+
+    a, b = S.diffwave_state_dict(1234), W.make_state_dict(1234)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    a, b = S.resnext_state_dict(4321), o_resnext.make_state_dict(4321)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(S.waveforms(3, 1000, seed=5), W.make_waveforms(3, 1000, seed=5))
+    assert torch.equal(S.noise((2, 3, 4), seed=9), W.make_noise((2, 3, 4), seed=9))

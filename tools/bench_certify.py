@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 import audiopure_b200 as ap  # noqa: E402
 from audiopure_b200.certified_robust import NcclCountsAllReduce  # noqa: E402
-from oracle import resnext as o_resnext, weights as W  # noqa: E402
+from audiopure_b200 import synthetic as S  # noqa: E402
 
 
 def main():
@@ -40,16 +40,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         allreduce = NcclCountsAllReduce(rank, world)
 
-    model = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
-    model.load_state_dict(W.make_state_dict(1234))
+    model = ap.WaveNet_Speech_Commands(**S.DEFAULT_WAVENET_CONFIG)
+    model.load_state_dict(S.diffwave_state_dict(1234))
     model = model.cuda().eval()
-    dw = ap.DiffWave(model, ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG), reverse_timestep=34)
+    dw = ap.DiffWave(model, ap.calc_diffusion_hyperparams(**S.DEFAULT_DIFFUSION_CONFIG), reverse_timestep=34)
     clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
-    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    clf.load_state_dict(S.resnext_state_dict(4321))
     clf = ap.FusedResNeXt(clf.cuda().eval()).cuda()
     RC = ap.RobustCertificate(clf, ap.LogMelSpectrogram().cuda(), dw, seed=5, rank=rank, world_size=world,
                               allreduce=allreduce)
-    x = W.make_waveforms(args.clips, 16000, seed=3).cuda()
+    x = S.waveforms(args.clips, 16000, seed=3).cuda()
     y = torch.zeros(args.clips, dtype=torch.long, device="cuda")
 
     # warm-up with the same batch shapes (cudnn.benchmark autotunes once per shape, remainder batches included)

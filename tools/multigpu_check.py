@@ -17,24 +17,24 @@ sys.path.insert(0, ROOT)
 
 import audiopure_b200 as ap  # noqa: E402
 from audiopure_b200.certified_robust import NcclCountsAllReduce, shard_range  # noqa: E402
-from oracle import resnext as o_resnext, weights as W  # noqa: E402
+from audiopure_b200 import synthetic as S  # noqa: E402
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
+    cfg = dict(S.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
     model = ap.WaveNet_Speech_Commands(**cfg)
-    model.load_state_dict(W.make_state_dict(99, cfg))
+    model.load_state_dict(S.diffwave_state_dict(99, cfg))
     model = model.cuda().eval()
-    hp = ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    hp = ap.calc_diffusion_hyperparams(**S.DEFAULT_DIFFUSION_CONFIG)
     dw = ap.DiffWave(model, hp, reverse_timestep=2)
     clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
-    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    clf.load_state_dict(S.resnext_state_dict(4321))
     clf = clf.cuda().eval()
     tr = ap.LogMelSpectrogram().cuda()
-    x = W.make_waveforms(1, 16000, seed=4)[0].cuda()
+    x = S.waveforms(1, 16000, seed=4)[0].cuda()
 
     n = 203
     allreduce = NcclCountsAllReduce(rank, world)
@@ -47,7 +47,7 @@ def main():
     print("rank %d: sharded counts %s %s unsharded %s" % (rank, counts.tolist(), "==" if ok1 else "!=", whole.tolist()), flush=True)
 
     B = 4 * world
-    xb = W.make_waveforms(B, 2048, seed=8).cuda()
+    xb = S.waveforms(B, 2048, seed=8).cuda()
     eng = model.engine()
     full = eng.ddpm_purify(xb, 3, seed=77)
     lo, hi = shard_range(B, rank, world)

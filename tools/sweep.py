@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import audiopure_b200 as ap  # noqa: E402
-from oracle import resnext as o_resnext, weights as W  # noqa: E402
+from audiopure_b200 import synthetic as S  # noqa: E402
 
 FLOP_PER_CLIP_EVAL = 606.10e9
 
@@ -30,19 +30,19 @@ def timed(fn, reps):
 
 def main():
     torch.backends.cudnn.benchmark = True
-    model = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
-    model.load_state_dict(W.make_state_dict(1234))
+    model = ap.WaveNet_Speech_Commands(**S.DEFAULT_WAVENET_CONFIG)
+    model.load_state_dict(S.diffwave_state_dict(1234))
     model = model.cuda().eval()
-    hp = ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    hp = ap.calc_diffusion_hyperparams(**S.DEFAULT_DIFFUSION_CONFIG)
     clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
-    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    clf.load_state_dict(S.resnext_state_dict(4321))
     clf = ap.FusedResNeXt(clf.cuda().eval()).cuda()
     tr = ap.LogMelSpectrogram().cuda()
     batches = [int(b) for b in (sys.argv[1].split(",") if len(sys.argv) > 1 else "1,2,4,8,16,32,64,128,256,1024".split(","))]
     tstars = [int(t) for t in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,2,3,5,10".split(","))]
     print("| batch | t* | purify ms | purify clips/s | network TFLOP/s | full step ms | full clips/s |\n|---|---|---|---|---|---|---|")
     for B in batches:
-        x = W.make_waveforms(B, 16000, seed=B).cuda()
+        x = S.waveforms(B, 16000, seed=B).cuda()
         for t in tstars:
             dw = ap.DiffWave(model, hp, reverse_timestep=t)
             system = ap.AcousticSystem(clf, tr, dw)

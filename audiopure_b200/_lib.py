@@ -76,6 +76,7 @@ SIGNATURES = {
     "ap_sde_purify": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _U64, _I64, _VP, _SZ, _VP]),
     "ap_one_shot": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "ap_logmel": (_I, [_VP, _I, _I, _VP, ctypes.POINTER(ApMelTables), _VP]),
+    "ap_logmel_backward": (_I, [_VP, _I, _I, _VP, _VP, ctypes.POINTER(ApMelTables), _VP]),
     "ap_smooth_inputs": (_I, [_VP, _I, _I, _F, _F, _VP, _U64, _U32, _I64, _VP, _VP]),
     "ap_vote_counts": (_I, [_VP, _I, _I, _VP, _VP]),
     "ap_comm_unique_id": (_I, [ctypes.c_char_p]),

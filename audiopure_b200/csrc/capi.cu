@@ -472,6 +472,33 @@ int ap_logmel(const float* x, int B, int L, float* out, const ap_mel_tables* tab
   return 0;
 }
 
+int ap_logmel_backward(const float* x, int B, int L, const float* grad_out, float* grad_x, const ap_mel_tables* tabs,
+                       void* stream) {
+  AP_CHECK(x && grad_out && grad_x && tabs, "null argument");
+  AP_CHECK(B > 0 && L > 0, "B and L must be positive");
+  AP_CHECK(L <= 40000, "ap_logmel_backward supports clips of at most 40000 samples");
+  AP_CHECK(tabs->n_mels > 0 && tabs->n_mels <= 128, "n_mels out of range");
+  ap::MelBwdArgs a;
+  a.x = x;
+  a.grad_out = grad_out;
+  a.grad_x = grad_x;
+  a.tw = static_cast<const float2*>(tabs->twiddles);
+  a.fb_start = tabs->fb_start;
+  a.fb_len = tabs->fb_len;
+  a.fb_off = tabs->fb_off;
+  a.fb_w = tabs->fb_w;
+  a.B = B;
+  a.L = L;
+  a.n_frames = 1 + L / ap::kHop;
+  a.n_mels = tabs->n_mels;
+  const size_t smem = static_cast<size_t>(L) * sizeof(float);
+  AP_CUDA(cudaFuncSetAttribute(ap::logmel_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)));
+  ap::logmel_backward_kernel<<<B, ap::kMelThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int ap_smooth_inputs(const float* x, int L, int n_draws, float sigma, float scale, const float* z, uint64_t seed,
                      uint32_t clip, int64_t first_draw, float* out, void* stream) {
   AP_CHECK(x && out, "null tensor");

@@ -58,6 +58,21 @@ def slaney_fbanks(n_mels=32, sample_rate=16000, f_min=0.0, f_max=None, n_freqs=N
     return fb * enorm.unsqueeze(0)
 
 
+class _LogMelFn(torch.autograd.Function):
+    """Forward: ap_logmel.  Backward: ap_logmel_backward (gradient w.r.t. the waveform only)."""
+
+    @staticmethod
+    def forward(ctx, x, module):
+        ctx.module = module
+        ctx.save_for_backward(x)
+        return module._forward(x)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        return ctx.module._backward(x, grad_out), None
+
+
 class LogMelSpectrogram(torch.nn.Module):
     """MelSpectrogram(n_fft=2048, hop=512, slaney/slaney, pad 'constant', power 2) + AmplitudeToDB('power')."""
 
@@ -83,19 +98,36 @@ class LogMelSpectrogram(torch.nn.Module):
         self.register_buffer("fb_off", torch.tensor(offs, dtype=torch.int32), persistent=False)
         self.register_buffer("fb_w", torch.tensor(weights, dtype=torch.float32), persistent=False)
 
+    def _tables(self):
+        return _lib.ApMelTables(self.twiddles.data_ptr(), self.fb_start.data_ptr(), self.fb_len.data_ptr(),
+                                self.fb_off.data_ptr(), self.fb_w.data_ptr(), self.n_mels)
+
     def forward(self, waveform):
-        lib = _lib.load()
         if waveform.device.type != "cuda":
             raise _lib.AudioPureError("LogMelSpectrogram runs on a CUDA device only (no CPU fallback)")
         if self.twiddles.device != waveform.device:
             self.to(waveform.device)
         assert waveform.ndim == 3 and waveform.shape[1] == 1, "expected (B, 1, L)"
-        x = waveform.to(torch.float32).contiguous()
+        if torch.is_grad_enabled() and waveform.requires_grad:  # gradient-based attacks through AcousticSystem
+            return _LogMelFn.apply(waveform, self)
+        return self._forward(waveform)
+
+    def _forward(self, waveform):
+        lib = _lib.load()
+        x = waveform.detach().to(torch.float32).contiguous()
         B, _, L = x.shape
-        n_frames = 1 + L // HOP
-        out = torch.empty(B, 1, self.n_mels, n_frames, dtype=torch.float32, device=x.device)
-        tabs = _lib.ApMelTables(self.twiddles.data_ptr(), self.fb_start.data_ptr(), self.fb_len.data_ptr(),
-                                self.fb_off.data_ptr(), self.fb_w.data_ptr(), self.n_mels)
+        out = torch.empty(B, 1, self.n_mels, 1 + L // HOP, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            _lib.check(lib.ap_logmel(x.data_ptr(), B, L, out.data_ptr(), tabs, _lib.stream_ptr()))
+            _lib.check(lib.ap_logmel(x.data_ptr(), B, L, out.data_ptr(), self._tables(), _lib.stream_ptr()))
         return out
+
+    def _backward(self, waveform, grad_out):
+        lib = _lib.load()
+        x = waveform.detach().to(torch.float32).contiguous()
+        g = grad_out.to(torch.float32).contiguous()
+        B, _, L = x.shape
+        grad_x = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.ap_logmel_backward(x.data_ptr(), B, L, g.data_ptr(), grad_x.data_ptr(), self._tables(),
+                                              _lib.stream_ptr()))
+        return grad_x.to(waveform.dtype)

@@ -119,6 +119,12 @@ typedef struct ap_mel_tables {
 } ap_mel_tables;
 int ap_logmel(const float* x, int B, int L, float* out, const ap_mel_tables* tabs, void* stream);
 
+/* Gradient of ap_logmel with respect to the waveform, for attacks that back-propagate through AcousticSystem
+ * (white_box_attack.py:392,437-439): grad_x[B][L] = d<grad_out, logmel(x)>/dx, grad_out: [B][n_mels][1 + L/512].
+ * L is limited by the per-clip shared-memory accumulator (L <= 40000).                                     */
+int ap_logmel_backward(const float* x, int B, int L, const float* grad_out, float* grad_x,
+                       const ap_mel_tables* tabs, void* stream);
+
 /* RobustCertificate.smooth_predict's input construction (certified_robust.py:46-54):
  *   out[j][l] = scale * (x[l] + sigma * z_j[l]),  j in [0, n_draws)
  * z: injected [n_draws][L], or NULL -> Philox keyed on (seed, clip, first_draw + j, l).                  */

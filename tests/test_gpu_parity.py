@@ -332,6 +332,36 @@ def test_logmel_ragged_lengths_and_silence():
     assert float(z.max()) == -100.0 and float(z.min()) == -100.0  # clamp at 1e-10 -> -100 dB
 
 
+def test_logmel_backward_vs_autograd_of_oracle():
+    from oracle import mel as o_mel
+
+    tr = ap.LogMelSpectrogram().cuda()
+    for L in (16000, 5000):
+        x = W.make_waveforms(2, L, seed=L + 1)
+        w = W.make_noise((2, 1, 32, 1 + L // 512), seed=3)
+        xo = x.clone().requires_grad_(True)
+        (o_mel.log_mel(xo) * w).sum().backward()
+        xg = x.cuda().requires_grad_(True)
+        (tr(xg) * w.cuda()).sum().backward()
+        assert rel_l2(xg.grad, xo.grad) < 1e-3, L
+
+
+def test_gradient_flows_through_acoustic_system(small_model, hp, classifier):
+    """The adaptive attack's backward pass (white_box_attack.py:392,437-439): loss -> classifier -> log-mel kernel
+    -> SDE purifier (linearised Jacobian) -> perturbation."""
+
+    class Args:
+        t, sample_step, rand_t, t_delta, use_bm, score_type = 2, 1, False, 0, False, "guided_diffusion"
+
+    rev = ap.RevDiffWave(Args(), model=ap.DiffWave(small_model, hp, reverse_timestep=2))
+    AS = ap.AcousticSystem(classifier=classifier, transform=ap.LogMelSpectrogram().cuda(), defender=rev)
+    x = W.make_waveforms(2, 16000, seed=13).cuda()
+    delta = torch.zeros_like(x, requires_grad=True)
+    loss = torch.nn.functional.cross_entropy(AS(x + delta), torch.tensor([1, 2], device="cuda"))
+    loss.backward()
+    assert delta.grad is not None and torch.isfinite(delta.grad).all() and float(delta.grad.abs().max()) > 0
+
+
 # ------------------------------------------------------------------------- composition and certification --
 def test_acoustic_system_vs_reference(full_model, hp, classifier, golden):
     g = golden("acoustic.npz")

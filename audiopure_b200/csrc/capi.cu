@@ -197,6 +197,18 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   const int units = (num_tiles + 1) / 2, clusters = n->num_sms / 2;
   const int grid = 2 * (units < clusters ? units : clusters);
   static const int dbg = getenv("AP_DEBUG") ? atoi(getenv("AP_DEBUG")) : 0;
+  // Programmatic dependent launch: each tensor-core kernel may begin its set-up (barriers, TMEM, descriptor
+  // prefetch) while its predecessor drains; griddepcontrol.wait in the kernel orders every global access.
+  static const bool pdl = getenv("AP_NO_PDL") == nullptr;
+  cudaLaunchConfig_t lc{};
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(ap::kThreads);
+  lc.stream = st;
+  lc.attrs = &attr;
+  lc.numAttrs = pdl ? 1 : 0;
   for (int l = 0; l < n->layers; ++l) {
     ap::LayerArgs a;
     a.L = L;
@@ -210,8 +222,9 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
     memcpy(bias.b1, n->h_b1.data() + static_cast<size_t>(l) * 512, sizeof(bias.b1));
     memcpy(bias.c2, n->h_c2.data() + (static_cast<size_t>(t) * n->layers + l) * ap::kC, sizeof(bias.c2));
     ProfSpan span(n, st, 0);
-    ap::layer_kernel<<<grid, ap::kThreads, ap::Tc::kLayerSmem, st>>>(n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
-                                                                     n->tm_h_st[(l + 1) & 1], bias, a);
+    lc.dynamicSmemBytes = ap::Tc::kLayerSmem;
+    AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
+                               n->tm_h_st[(l + 1) & 1], bias, a));
   }
   tail.bs = n->w.bs;
   tail.bf = n->w.bf;
@@ -224,7 +237,8 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   tail.num_layers = n->layers;
   {
     ProfSpan span(n, st, 1);
-    ap::tail_kernel<<<grid, ap::kThreads, ap::Tc::kTailSmem, st>>>(n->tm_gate, n->tm_ws, n->tm_wf, tail);
+    lc.dynamicSmemBytes = ap::Tc::kTailSmem;
+    AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel, n->tm_gate, n->tm_ws, n->tm_wf, tail));
   }
   AP_CUDA(cudaGetLastError());
   return 0;

@@ -238,6 +238,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();  // the next launch may set itself up while this one runs ...
+  pdl_wait();               // ... and nothing below touches global memory before the previous launch is complete
 
   if (warp == 0) {
     // ======================= TMA producer (whole warp walks the loop; one elected lane issues) ==========
@@ -556,6 +558,8 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int total_ks = a.num_layers * 4;
   const int J = total_ks / 2 < 16 ? total_ks / 2 : 16;  // where the previous tile's head GEMM is slotted in

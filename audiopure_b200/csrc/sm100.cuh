@@ -282,6 +282,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// ------------------------------------------------ programmatic dependent launch (PDL) --
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream is still running; pdl_wait() blocks until that predecessor has completed and its writes are
+// visible.  Everything before it (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's
+// tail.  pdl_launch_dependents() lets the successor start being scheduled as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------- maths --
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

@@ -149,6 +149,17 @@ def stage_b64():
     print("  layer kernel: %.1f TFLOP/s (14.68 GFLOP/clip)" % (64 * 14.68e9 / (lms * 1e-3) / 1e12))
     tms = prof["tail"][0]
     print("  tail kernel: %.1f TFLOP/s (77.6 GFLOP/clip)" % (64 * 77.6e9 / (tms * 1e-3) / 1e12))
+    for B in (64, 4, 1):
+        xb = x[:B]
+        eng.eps(xb, 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5 if B == 64 else 20
+        e0.record()
+        for _ in range(reps):
+            eng.eps(xb, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        print("  unprofiled eval B=%d: %.3f ms" % (B, e0.elapsed_time(e1) / reps))
 
 
 if __name__ == "__main__":

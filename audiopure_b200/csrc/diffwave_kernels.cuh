@@ -149,6 +149,23 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_tiles, int til
   return t;
 }
 
+// A conv tap whose 128-row window lies entirely in the zero padding contributes nothing: with dilation 2048 that
+// is a third of GEMM1 for a quarter of a clip's tiles.  The K steps of such a tap are skipped when the window is
+// dead for BOTH tiles of the pair (they share the MMA), by the TMA and MMA warps alike.
+__device__ __forceinline__ bool tap_window_live(const TileCoord& t, int tap, int dilation, int L) {
+  const int lo = t.l0 + (tap - 1) * dilation;
+  return t.valid && lo + kTileT > 0 && lo < L;
+}
+__device__ __forceinline__ uint32_t live_tap_mask(int unit, int num_tiles, int tiles_per_clip, int dilation, int L) {
+  const TileCoord t0 = tile_coord(2 * unit, num_tiles, tiles_per_clip);
+  const TileCoord t1 = tile_coord(2 * unit + 1, num_tiles, tiles_per_clip);
+  uint32_t m = 0;
+#pragma unroll
+  for (int tap = 0; tap < 3; ++tap)
+    if (tap_window_live(t0, tap, dilation, L) || tap_window_live(t1, tap, dilation, L)) m |= 1u << tap;
+  return m;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K1: one residual layer (WaveNet.py:75-97), fully fused, persistent over pairs of 128-step tiles.
 //
@@ -248,8 +265,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     uint32_t it = 0;
     for (int u = unit0; 2 * u < a.num_tiles; u += units) {
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
+      const uint32_t live = live_tap_mask(u, a.num_tiles, a.tiles_per_clip, a.dilation, a.L);
       for (int c = 0; c < 2; ++c) {
-        for (int ks = 0; ks < 12; ++ks, ++it) {
+        for (int ks = 0; ks < 12; ++ks) {
+          if (!((live >> (ks >> 2)) & 1)) continue;
           const int s = it % kStages;
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 1);
           if (elect_one()) {
@@ -260,6 +279,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
             tma_load_2d_pair(sa + kABytes, &tm_w1, full0 + 8 * s, ks * 64, a.layer * 512 + c * 256 + brow);
           }
           __syncwarp();
+          ++it;
         }
       }
       for (int ks = 0; ks < 4; ++ks, ++it) {
@@ -283,13 +303,17 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
         const uint32_t p = i & 1;
         const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
+        const uint32_t live = live_tap_mask(u, a.num_tiles, a.tiles_per_clip, a.dilation, a.L);
+        const int last_ks = 4 * (31 - __clz(live)) + 3;  // the centre tap is live for any real tile
         for (int c = 0; c < 2; ++c) {
           if (c == 1 && i > 0) {  // bufB held the previous tile's residual accumulator
             mbar_wait(d2_empty, (i - 1) & 1, 3);
             tc_fence_after();
           }
           const uint32_t d = c ? bufB : bufA;
-          for (int ks = 0; ks < 12; ++ks, ++it) {
+          uint32_t acc = 0;  // the first MMA issued into the buffer overwrites it
+          for (int ks = 0; ks < 12; ++ks) {
+            if (!((live >> (ks >> 2)) & 1)) continue;
             const int s = it % kStages;
             mbar_wait(&full[s], (it / kStages) & 1, 4);
             tc_fence_after();
@@ -297,11 +321,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
               const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
               const uint64_t db = da + static_cast<uint64_t>(kABytes >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, acc | k);
               umma_commit_pair(&empty[s]);
-              if (ks == 11) umma_commit_pair(&d1_full[c]);
+              if (ks == last_ks) umma_commit_pair(&d1_full[c]);
             }
             __syncwarp();
+            acc = 1;
+            ++it;
           }
         }
         for (int ks = 0; ks < 4; ++ks, ++it) {

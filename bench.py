@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--t-star", type=int, default=T_STAR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clips", type=int, default=1)
+    ap.add_argument("--purifier", default="ddpm", choices=["ddpm", "sde"],
+                    help="ddpm: DiffWave.forward (BASELINE configs[1], the headline); sde: RevDiffWave (configs[2])")
     ap.add_argument("--classifier", default="fused", choices=["fused", "module"],
                     help="consumer ResNeXt-29: bf16 channels-last with folded batch-norm, or the plain fp32 nn.Module")
     return ap.parse_args()
@@ -161,9 +163,10 @@ def run_reference(args):
 
 def workload_config(args):
     return {
-        "workload": "BASELINE configs[1]: DDPM t*=%d purification + log-mel + ResNeXt-29 8x64, batch %d synthetic "
+        "workload": "BASELINE configs[%d]: %s t*=%d purification + log-mel + ResNeXt-29 8x64, batch %d synthetic "
                     "1-s 16 kHz clips per GPU, DiffWave-unconditional (36 layers, 256 ch, T=200), random-init weights"
-                    % (args.t_star, args.batch),
+                    % (1 if args.purifier == "ddpm" else 2, "DDPM" if args.purifier == "ddpm" else "reverse VP-SDE",
+                       args.t_star, args.batch),
         "batch_per_gpu": args.batch, "t_star": args.t_star, "clip_samples": CLIP_LEN,
         "classifier": "ResNeXt-29 8x64 consumer (cuDNN): " + ("bf16 channels-last, batch-norm folded" if args.classifier == "fused" else "fp32 nn.Module"),
         "l2": "no flush needed: every step streams a ~20 GB activation workspace, far larger than the 126 MB L2",
@@ -192,6 +195,10 @@ def run_ours(args):
     model = model.to(dev).eval()
     hp = ap.calc_diffusion_hyperparams(**S.DEFAULT_DIFFUSION_CONFIG)
     defender = ap.DiffWave(model, hp, reverse_timestep=args.t_star, seed=rank)
+    if args.purifier == "sde":
+        sde_args = type("Args", (), dict(t=args.t_star, sample_step=1, rand_t=False, t_delta=0, use_bm=False,
+                                         score_type="guided_diffusion"))()
+        defender = ap.RevDiffWave(sde_args, device=dev, model=defender, seed=rank)
     clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
     clf.load_state_dict(S.resnext_state_dict(4321))
     clf = clf.to(dev).eval()

@@ -436,6 +436,18 @@ def test_certify_end_to_end_and_abstain(small_model, hp, classifier):
     assert torch.equal(y_pred, y2) and torch.equal(radius, r2)
 
 
+def test_randsmooth_baseline_without_denoiser(classifier):
+    """certified_robustness_eval.py:88-89 (`--defense_method randsmooth`): no denoiser, no sqrt(alpha_bar) scaling."""
+    tr = ap.LogMelSpectrogram().cuda()
+    x = W.make_waveforms(1, 16000, seed=5)[0].cuda()
+    z = W.make_noise((10, 1, 16000), seed=6)
+    RC = ap.RobustCertificate(classifier, tr, denoiser=None)
+    counts = RC.smooth_predict(x, 10, 0.5, batch_size=4, z=z)
+    x_in = x.cpu().repeat(10, 1, 1) + 0.5 * z
+    want = o_certify.vote_counts(o_resnext.forward(o_resnext.make_state_dict(4321), __import__("oracle").mel.log_mel(x_in)), 10)
+    assert torch.equal(counts, want)
+
+
 def test_sharded_counts_equal_single_rank(small_model, hp, classifier):
     """Two logical ranks on one GPU: disjoint draw slices, summed counts == the unsharded counts."""
     dw = ap.DiffWave(small_model, hp, reverse_timestep=2)

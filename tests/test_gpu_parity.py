@@ -384,6 +384,30 @@ def test_acoustic_system_vs_reference(full_model, hp, classifier, golden):
         ap.AcousticSystem(classifier, None, dw, defense_type="other")
 
 
+def test_pipeline_agreement_on_a_batch_of_synthetic_clips(full_model, hp, classifier):
+    """BASELINE config 1 shape (DDPM t*=2 -> log-mel -> ResNeXt-29) on 8 clips against the CPU oracle with the same
+    injected noise: waveform gate, logits, and top-1 agreement (north star: >= 99.5 %)."""
+    from oracle import mel as o_mel
+
+    B, t_star = 8, 2
+    x = W.make_waveforms(B, 16000, seed=31)
+    z = W.make_noise((t_star, B, 1, 16000), seed=32)
+    sd, csd = W.make_state_dict(1234), o_resnext.make_state_dict(4321)
+    o_hp = o_schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    with torch.no_grad():
+        want_wave = o_purify.ddpm_purify(o_hp, lambda xx, t: o_wavenet.eps_theta(sd, xx, t), x, t_star, z)
+        want_logits = o_resnext.forward(csd, o_mel.log_mel(want_wave))
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=t_star)
+    AS = ap.AcousticSystem(classifier, ap.LogMelSpectrogram().cuda(), defender=None)
+    with torch.no_grad():
+        got_wave = dw(x.cuda(), z=z)
+        got_logits = AS(got_wave)
+    assert rel_l2(got_wave, want_wave) < WAVE_GATE
+    assert float((got_wave.cpu() - want_wave).abs().max()) < 1e-3
+    assert rel_l2(got_logits, want_logits) < 5e-2
+    assert float((got_logits.argmax(1).cpu() == want_logits.argmax(1)).float().mean()) >= 0.995
+
+
 def test_fused_bf16_classifier_agrees_with_fp32(classifier):
     """North star: classifier top-1 agreement >= 99.5 % on synthetic clips (bf16 fused consumer vs fp32 module)."""
     fused = ap.FusedResNeXt(classifier).cuda()

@@ -13,7 +13,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 c_i32_p = ctypes.POINTER(ctypes.c_int32)
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 
-AP_ABI_VERSION = 2
+AP_ABI_VERSION = 3
 AP_COMM_ID_BYTES = 128
 
 
@@ -58,6 +58,7 @@ class ApMelTables(ctypes.Structure):
         ("fb_off", ctypes.c_void_p),
         ("fb_w", ctypes.c_void_p),
         ("n_mels", ctypes.c_int32),
+        ("fb_nnz", ctypes.c_int32),
     ]
 
 

@@ -468,7 +468,9 @@ int ap_logmel(const float* x, int B, int L, float* out, const ap_mel_tables* tab
   AP_CHECK(x && out && tabs, "null argument");
   AP_CHECK(B > 0 && L > 0, "B and L must be positive");
   AP_CHECK(tabs->n_mels > 0 && tabs->n_mels <= 128, "n_mels out of range");
+  AP_CHECK(tabs->fb_nnz > 0 && tabs->fb_nnz <= ap::kMaxFbNnz, "fb_nnz out of range");
   ap::MelArgs a;
+  a.fb_nnz = tabs->fb_nnz;
   a.x = x;
   a.out = out;
   a.tw = static_cast<const float2*>(tabs->twiddles);
@@ -492,6 +494,7 @@ int ap_logmel_backward(const float* x, int B, int L, const float* grad_out, floa
   AP_CHECK(B > 0 && L > 0, "B and L must be positive");
   AP_CHECK(L <= 40000, "ap_logmel_backward supports clips of at most 40000 samples");
   AP_CHECK(tabs->n_mels > 0 && tabs->n_mels <= 128, "n_mels out of range");
+  AP_CHECK(tabs->fb_nnz > 0 && tabs->fb_nnz <= ap::kMaxFbNnz, "fb_nnz out of range");
   ap::MelBwdArgs a;
   a.x = x;
   a.grad_out = grad_out;

@@ -18,6 +18,18 @@ constexpr int kNfft = 2048;
 constexpr int kHop = 512;
 constexpr int kBins = kNfft / 2 + 1;
 constexpr int kMelThreads = 256;
+constexpr int kMaxFbNnz = 2304;  // filterbank weights staged in shared memory
+constexpr int kFftPad = kNfft + kNfft / 32;  // one float2 of skew per 32 elements: de-conflicts the bit-reversed scatter
+
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 5); }
+
+// exp(-i * 2*pi*k/2048) for the butterflies.  The shared twiddle table is only read with unit stride (window);
+// the strided butterfly reads (up to 32-way bank conflicts) are replaced by two MUFU ops (abs. error 2^-21).
+__device__ __forceinline__ float2 twiddle(int k) {
+  float sn, cs;
+  __sincosf(-3.14159265358979323846f * static_cast<float>(k) * (1.0f / 1024.0f), &sn, &cs);
+  return make_float2(cs, sn);
+}
 
 struct MelArgs {
   const float* x;        // [B][L]
@@ -27,15 +39,44 @@ struct MelArgs {
   const int* fb_len;     // [n_mels] number of consecutive non-zero bins
   const int* fb_off;     // [n_mels] offset of that run in fb_w
   const float* fb_w;     // concatenated non-zero weights
-  int B, L, n_frames, n_mels;
+  int B, L, n_frames, n_mels, fb_nnz;
 };
 
+// In-place 2048-point radix-2 DIT FFT on bit-reversed input held in (padded) shared memory.
+// sign = +1: forward (e^{-i...}); sign = -1: unnormalised inverse (conjugated twiddles).
+__device__ __forceinline__ void fft2048_inplace(float2* zs, int tid, float sign) {
+#pragma unroll 1
+  for (int s = 0; s < 11; ++s) {
+    const int half = 1 << s;
+    for (int j = tid; j < kNfft / 2; j += kMelThreads) {
+      const int pos = j & (half - 1);
+      const int i0 = ((j >> s) << (s + 1)) + pos;
+      const int i1 = i0 + half;
+      float2 t = twiddle(pos << (10 - s));
+      t.y *= sign;
+      const float2 u = zs[fpad(i0)], v = zs[fpad(i1)];
+      const float2 vt = make_float2(v.x * t.x - v.y * t.y, v.x * t.y + v.y * t.x);
+      zs[fpad(i0)] = make_float2(u.x + vt.x, u.y + vt.y);
+      zs[fpad(i1)] = make_float2(u.x - vt.x, u.y - vt.y);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
-  __shared__ float2 zs[kNfft];
+  __shared__ float2 zs[kFftPad];
   __shared__ float2 tws[kNfft / 2];
   __shared__ float pw[2][kBins + 3];
+  __shared__ float fbw[kMaxFbNnz];  // a global read per filter tap made the mel reduction latency-bound (29 of 42 us)
+  __shared__ int fbd[3][128];
 
   const int tid = threadIdx.x;
+  for (int i = tid; i < a.fb_nnz; i += kMelThreads) fbw[i] = a.fb_w[i];
+  for (int i = tid; i < a.n_mels; i += kMelThreads) {
+    fbd[0][i] = a.fb_start[i];
+    fbd[1][i] = a.fb_len[i];
+    fbd[2][i] = a.fb_off[i];
+  }
   const int pairs = (a.n_frames + 1) >> 1;
   const int b = blockIdx.x / pairs;
   const int f0 = (blockIdx.x - b * pairs) * 2;
@@ -53,29 +94,14 @@ __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
     const int i2 = i1 + kHop;
     const float v1 = (i1 >= 0 && i1 < a.L) ? __ldg(x + i1) : 0.f;
     const float v2 = (has2 && i2 >= 0 && i2 < a.L) ? __ldg(x + i2) : 0.f;
-    zs[__brev(static_cast<unsigned>(n)) >> 21] = make_float2(v1 * w, v2 * w);
+    zs[fpad(__brev(static_cast<unsigned>(n)) >> 21)] = make_float2(v1 * w, v2 * w);
   }
   __syncthreads();
-
-#pragma unroll 1
-  for (int s = 0; s < 11; ++s) {
-    const int half = 1 << s;
-    for (int j = tid; j < kNfft / 2; j += kMelThreads) {
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> s) << (s + 1)) + pos;
-      const int i1 = i0 + half;
-      const float2 t = tws[pos << (10 - s)];
-      const float2 u = zs[i0], v = zs[i1];
-      const float2 vt = make_float2(v.x * t.x - v.y * t.y, v.x * t.y + v.y * t.x);
-      zs[i0] = make_float2(u.x + vt.x, u.y + vt.y);
-      zs[i1] = make_float2(u.x - vt.x, u.y - vt.y);
-    }
-    __syncthreads();
-  }
+  fft2048_inplace(zs, tid, 1.f);
 
   // Z = F1 + i*F2  ->  F1[k] = (Z[k] + conj(Z[N-k]))/2,  F2[k] = (Z[k] - conj(Z[N-k]))/(2i)
   for (int k = tid; k < kBins; k += kMelThreads) {
-    const float2 zk = zs[k], zn = zs[(kNfft - k) & (kNfft - 1)];
+    const float2 zk = zs[fpad(k)], zn = zs[fpad((kNfft - k) & (kNfft - 1))];
     const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
     const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
     pw[0][k] = ar * ar + ai * ai;
@@ -86,9 +112,9 @@ __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
   const int warp = tid >> 5, lane = tid & 31;
   for (int o = warp; o < 2 * a.n_mels; o += kMelThreads / 32) {
     const int fr = o / a.n_mels, m = o - fr * a.n_mels;
-    const int start = a.fb_start[m], len = a.fb_len[m], off = a.fb_off[m];
+    const int start = fbd[0][m], len = fbd[1][m], off = fbd[2][m];
     float acc = 0.f;
-    for (int i = lane; i < len; i += 32) acc = fmaf(a.fb_w[off + i], pw[fr][start + i], acc);
+    for (int i = lane; i < len; i += 32) acc = fmaf(fbw[off + i], pw[fr][start + i], acc);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     if (lane == 0 && (fr == 0 || has2))
@@ -116,29 +142,9 @@ struct MelBwdArgs {
   int B, L, n_frames, n_mels;
 };
 
-__device__ __forceinline__ void fft2048_inplace(float2* zs, const float2* tws, int tid, float sign) {
-  // radix-2 DIT on bit-reversed input; sign = +1 forward (e^{-i...}), -1 inverse (conjugated twiddles)
-#pragma unroll 1
-  for (int s = 0; s < 11; ++s) {
-    const int half = 1 << s;
-    for (int j = tid; j < kNfft / 2; j += kMelThreads) {
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> s) << (s + 1)) + pos;
-      const int i1 = i0 + half;
-      float2 t = tws[pos << (10 - s)];
-      t.y *= sign;
-      const float2 u = zs[i0], v = zs[i1];
-      const float2 vt = make_float2(v.x * t.x - v.y * t.y, v.x * t.y + v.y * t.x);
-      zs[i0] = make_float2(u.x + vt.x, u.y + vt.y);
-      zs[i1] = make_float2(u.x - vt.x, u.y - vt.y);
-    }
-    __syncthreads();
-  }
-}
-
 __global__ void __launch_bounds__(kMelThreads) logmel_backward_kernel(const MelBwdArgs a) {
   extern __shared__ float gacc[];  // [L] gradient of this clip
-  __shared__ float2 zs[kNfft];
+  __shared__ float2 zs[kFftPad];
   __shared__ float2 tws[kNfft / 2];
   __shared__ float2 spec[2][kBins];  // X of the two frames, then Z = 2 dP X
   __shared__ float dmel[2][128];
@@ -159,12 +165,12 @@ __global__ void __launch_bounds__(kMelThreads) logmel_backward_kernel(const MelB
       const int i1 = f0 * kHop - kNfft / 2 + n, i2 = i1 + kHop;
       const float v1 = (i1 >= 0 && i1 < a.L) ? __ldg(x + i1) : 0.f;
       const float v2 = (has2 && i2 >= 0 && i2 < a.L) ? __ldg(x + i2) : 0.f;
-      zs[__brev(static_cast<unsigned>(n)) >> 21] = make_float2(v1 * w, v2 * w);
+      zs[fpad(__brev(static_cast<unsigned>(n)) >> 21)] = make_float2(v1 * w, v2 * w);
     }
     __syncthreads();
-    fft2048_inplace(zs, tws, tid, 1.f);
+    fft2048_inplace(zs, tid, 1.f);
     for (int k = tid; k < kBins; k += kMelThreads) {
-      const float2 zk = zs[k], zn = zs[(kNfft - k) & (kNfft - 1)];
+      const float2 zk = zs[fpad(k)], zn = zs[fpad((kNfft - k) & (kNfft - 1))];
       spec[0][k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
       spec[1][k] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
     }
@@ -218,16 +224,16 @@ __global__ void __launch_bounds__(kMelThreads) logmel_backward_kernel(const MelB
         h1 = make_float2(0.5f * spec[0][kk].x, -0.5f * spec[0][kk].y);
         h2 = make_float2(0.5f * spec[1][kk].x, -0.5f * spec[1][kk].y);
       }
-      zs[__brev(static_cast<unsigned>(k)) >> 21] = make_float2(h1.x - h2.y, h1.y + h2.x);  // H1 + i*H2
+      zs[fpad(__brev(static_cast<unsigned>(k)) >> 21)] = make_float2(h1.x - h2.y, h1.y + h2.x);  // H1 + i*H2
     }
     __syncthreads();
-    fft2048_inplace(zs, tws, tid, -1.f);
+    fft2048_inplace(zs, tid, -1.f);
     // ---- window and overlap-add (frames f0 and f0+1 touch disjoint phases of this loop: one sync between) ----
     for (int n = tid; n < kNfft; n += kMelThreads) {
       const float c = (n < kNfft / 2) ? tws[n].x : -tws[n - kNfft / 2].x;
       const float w = 0.5f - 0.5f * c;
       const int i1 = f0 * kHop - kNfft / 2 + n;
-      if (i1 >= 0 && i1 < a.L) gacc[i1] += w * zs[n].x;
+      if (i1 >= 0 && i1 < a.L) gacc[i1] += w * zs[fpad(n)].x;
     }
     __syncthreads();
     if (has2) {
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(kMelThreads) logmel_backward_kernel(const MelB
         const float c = (n < kNfft / 2) ? tws[n].x : -tws[n - kNfft / 2].x;
         const float w = 0.5f - 0.5f * c;
         const int i2 = (f0 + 1) * kHop - kNfft / 2 + n;
-        if (i2 >= 0 && i2 < a.L) gacc[i2] += w * zs[n].y;
+        if (i2 >= 0 && i2 < a.L) gacc[i2] += w * zs[fpad(n)].y;
       }
     }
     __syncthreads();

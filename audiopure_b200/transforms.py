@@ -100,7 +100,7 @@ class LogMelSpectrogram(torch.nn.Module):
 
     def _tables(self):
         return _lib.ApMelTables(self.twiddles.data_ptr(), self.fb_start.data_ptr(), self.fb_len.data_ptr(),
-                                self.fb_off.data_ptr(), self.fb_w.data_ptr(), self.n_mels)
+                                self.fb_off.data_ptr(), self.fb_w.data_ptr(), self.n_mels, int(self.fb_w.numel()))
 
     def forward(self, waveform):
         if waveform.device.type != "cuda":

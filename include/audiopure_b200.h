@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AP_ABI_VERSION 2
+#define AP_ABI_VERSION 3
 
 typedef struct ap_net ap_net;   /* the packed DiffWave epsilon-network + its diffusion schedule */
 typedef struct ap_comm ap_comm; /* an NCCL communicator for the vote-count all-reduce           */
@@ -116,6 +116,7 @@ typedef struct ap_mel_tables {
   const int32_t* fb_off;   /* [n_mels] */
   const float* fb_w;       /* concatenated non-zero filterbank weights */
   int32_t n_mels;
+  int32_t fb_nnz;          /* number of floats in fb_w (<= 2304: every bin belongs to at most two triangular filters) */
 } ap_mel_tables;
 int ap_logmel(const float* x, int B, int L, float* out, const ap_mel_tables* tabs, void* stream);
 

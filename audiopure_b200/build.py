@@ -39,11 +39,13 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    """Compile if missing or older than its sources. Returns the library path."""
+def build(force=False, verbose=False, ablation=False):
+    """Compile if missing or older than its sources. Returns the library path.
+    ablation=True adds -DAP_ENABLE_ABLATION (the AP_DEBUG switches used for profiles/r01_ablation.md)."""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + LINK
+    cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DAP_ENABLE_ABLATION"] if ablation else [])
+           + ["-o", LIB] + SOURCES + LINK)
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
@@ -53,4 +55,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--ablation" in sys.argv, verbose="-v" in sys.argv,
+                ablation="--ablation" in sys.argv))

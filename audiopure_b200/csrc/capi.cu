@@ -196,7 +196,13 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   // persistent grid of CTA pairs (clusters of 2, one per TPC); each pair walks pairs of tiles
   const int units = (num_tiles + 1) / 2, clusters = n->num_sms / 2;
   const int grid = 2 * (units < clusters ? units : clusters);
+  // Ablation switches of profiles/r01_ablation.md change results; they exist only in builds made with
+  // -DAP_ENABLE_ABLATION (python -m audiopure_b200.build --ablation), never in the default library.
+#ifdef AP_ENABLE_ABLATION
   static const int dbg = getenv("AP_DEBUG") ? atoi(getenv("AP_DEBUG")) : 0;
+#else
+  const int dbg = 0;
+#endif
   // Programmatic dependent launch: each tensor-core kernel may begin its set-up (barriers, TMEM, descriptor
   // prefetch) while its predecessor drains; griddepcontrol.wait in the kernel orders every global access.
   static const bool pdl = getenv("AP_NO_PDL") == nullptr;

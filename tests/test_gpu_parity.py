@@ -157,6 +157,23 @@ def test_eps_odd_length_and_tiny_clip(small_model):
         assert rel_l2(got, o_wavenet.eps_theta(sd, x, 4, SMALL)) < EPS_GATE, (B, L)
 
 
+@pytest.mark.parametrize("layers,cycle,B,L,t", [
+    (1, 1, 1, 64, 0), (2, 2, 2, 127, 5), (3, 3, 5, 300, 17), (5, 5, 1, 2049, 100), (12, 12, 2, 700, 3),
+    (12, 12, 1, 4100, 199), (4, 2, 4, 1536, 8), (7, 7, 3, 257, 60),
+])
+def test_eps_random_architectures_and_shapes(layers, cycle, B, L, t):
+    """Depths, dilation cycles (up to dilation 2048 > L: every outer tap window is dead), odd batch sizes and ragged
+    lengths against the dataflow emulation -- exercises dummy tiles of odd pairs, partial tiles and skipped taps."""
+    cfg = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=layers, dilation_cycle=cycle)
+    m = make_model(cfg, 1000 + layers)
+    x = W.make_waveforms(B, L, seed=L)
+    got = m.engine().eps(x.cuda(), t).cpu()
+    packed = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in m.engine().packed.items()}
+    emu = emulate_eps(packed, x, t, layers, cycle, quantize=True)
+    assert got.shape == (B, 1, L) and torch.isfinite(got).all()
+    assert rel_l2(got, emu) < 8e-3, rel_l2(got, emu)
+
+
 def test_eps_chunking_over_max_chunk():
     m = ap.WaveNet_Speech_Commands(**SMALL, max_chunk=2)
     m.load_state_dict(W.make_state_dict(99, SMALL))

@@ -13,7 +13,8 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 c_i32_p = ctypes.POINTER(ctypes.c_int32)
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 
-AP_ABI_VERSION = 3
+AP_ABI_VERSION = 4
+AP_FLAG_TF32 = 1
 AP_COMM_ID_BYTES = 128
 
 
@@ -87,6 +88,8 @@ SIGNATURES = {
     "ap_profile_enable": (_I, [_VP, _I]),
     "ap_profile_read": (_I, [_VP, ctypes.POINTER(ctypes.c_double), c_i64_p]),
     "ap_debug_gemm": (_I, [_VP, _VP, _VP, _I, _VP]),
+    "ap_debug_gemm_tf32": (_I, [_VP, _VP, _VP, _I, _VP]),
+    "ap_precision": (_I, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint32)]),
 }
 
 _lib = None

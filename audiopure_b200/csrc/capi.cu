@@ -53,23 +53,23 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// bf16 tensor, innermost dim contiguous, box = {64 elements (128 B), box1, 1, ...}, 128-byte swizzle,
-// out-of-bounds elements read as zero.
-int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, uint32_t box1) {
+// bf16 (or, for the tf32 build, fp32) tensor, innermost dim contiguous, box = {128 bytes of elements, box1, 1, ...},
+// 128-byte swizzle, out-of-bounds elements read as zero.
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, uint32_t box1, bool f32 = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   AP_CHECK(fn, "cuTensorMapEncodeTiled entry point not available from the driver");
   cuuint64_t gdim[5];
   cuuint64_t gstride[4];
   cuuint32_t box[5], estr[5];
-  uint64_t stride = 2;
+  uint64_t stride = f32 ? 4 : 2;
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     stride *= dims[i];
     if (i < rank - 1) gstride[i] = stride;
-    box[i] = (i == 0) ? 64 : (i == 1 ? box1 : 1);
+    box[i] = (i == 0) ? (f32 ? 32 : 64) : (i == 1 ? box1 : 1);
     estr[i] = 1;
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
@@ -82,7 +82,10 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct ap_net {
   int layers = 0, cycle = 0, T = 0, max_chunk = 64;
-  std::vector<float> h_b1, h_c2;  // host copies of the bias tables (passed to the layer kernel by value)
+  bool tf32 = false;          // AP_FLAG_TF32: fp32 storage + kind::tf32 MMAs instead of bf16
+  uint32_t round_bias = 0;    // tf32: added to fp32 operand bits so that the tensor core's narrowing rounds to nearest
+  std::vector<float> h_b1, h_c2;  // host copies of the bias tables (passed to the kernels by value)
+  ap::TailBias tail_bias{};
   ap_weights w{};
   std::vector<float> alpha, alpha_bar, sigma, sde_beta, sde_acp;
   CUtensorMap tm_w1, tm_w2, tm_ws, tm_wf;
@@ -146,7 +149,7 @@ struct WsLayout {
 
 WsLayout ws_layout(const ap_net* n, int Bc, int L) {
   WsLayout w;
-  w.h_bytes = static_cast<size_t>(Bc) * L * ap::kC * 2;  // a multiple of 512: enough for TMA (16 B) and 128 B lines
+  w.h_bytes = static_cast<size_t>(Bc) * L * ap::kC * (n->tf32 ? 4 : 2);  // a multiple of 512: enough for TMA (16 B) and 128 B lines
   w.off_h[0] = 0;
   w.off_h[1] = w.h_bytes;
   w.off_gate = 2 * w.h_bytes;
@@ -162,11 +165,13 @@ int ensure_maps(ap_net* n, uint8_t* ws, int Bc, int L) {
   const WsLayout w = ws_layout(n, Bc, L);
   const uint64_t d3[3] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc)};
   for (int i = 0; i < 2; ++i)
-    if (make_map(&n->tm_h[i], ws + w.off_h[i], 3, d3, ap::kTileT) || make_map(&n->tm_h_st[i], ws + w.off_h[i], 3, d3, 32))
+    if (make_map(&n->tm_h[i], ws + w.off_h[i], 3, d3, ap::kTileT, n->tf32) ||
+        make_map(&n->tm_h_st[i], ws + w.off_h[i], 3, d3, 32, n->tf32))
       return 1;
   const uint64_t d4[4] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc),
                           static_cast<uint64_t>(n->layers)};
-  if (make_map(&n->tm_gate, ws + w.off_gate, 4, d4, ap::kTileT) || make_map(&n->tm_gate_st, ws + w.off_gate, 4, d4, 32))
+  if (make_map(&n->tm_gate, ws + w.off_gate, 4, d4, ap::kTileT, n->tf32) ||
+      make_map(&n->tm_gate_st, ws + w.off_gate, 4, d4, 32, n->tf32))
     return 1;
   n->cached_ws = ws;
   n->cached_B = Bc;
@@ -179,17 +184,19 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   AP_CHECK(t >= 0 && t < n->T, "diffusion step t out of range [0, T)");
   if (ensure_maps(n, ws, Bc, L)) return 1;
   const WsLayout w = ws_layout(n, Bc, L);
-  __nv_bfloat16* h[2] = {reinterpret_cast<__nv_bfloat16*>(ws + w.off_h[0]),
-                         reinterpret_cast<__nv_bfloat16*>(ws + w.off_h[1])};
+  void* h0 = ws + w.off_h[0];
   const long long rows = static_cast<long long>(Bc) * L;
   {
     long long blocks = (rows + 7) / 8;
     const long long cap = static_cast<long long>(n->num_sms) * 16;
     if (blocks > cap) blocks = cap;
     ProfSpan span(n, st, 2);
-    ap::prologue_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->w.w0, n->w.b0,
-                                                                        n->w.part0 + static_cast<size_t>(t) * ap::kC,
-                                                                        h[0], rows);
+    const float* part0 = n->w.part0 + static_cast<size_t>(t) * ap::kC;
+    if (n->tf32)
+      ap::prologue_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->w.w0, n->w.b0, part0, h0, rows,
+                                                                                n->round_bias);
+    else
+      ap::prologue_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n->w.w0, n->w.b0, part0, h0, rows, 0u);
   }
   const int tiles_per_clip = (L + ap::kTileT - 1) / ap::kTileT;
   const int num_tiles = tiles_per_clip * Bc;
@@ -224,18 +231,23 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
     a.layer = l;
     a.write_h = (l + 1 < n->layers) ? 1 : 0;
     a.debug = dbg;
+    a.round_bias = n->round_bias;
     ap::LayerBias bias;
     memcpy(bias.b1, n->h_b1.data() + static_cast<size_t>(l) * 512, sizeof(bias.b1));
     memcpy(bias.c2, n->h_c2.data() + (static_cast<size_t>(t) * n->layers + l) * ap::kC, sizeof(bias.c2));
     ProfSpan span(n, st, 0);
-    lc.dynamicSmemBytes = ap::Tc::kLayerSmem;
-    AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
-                               n->tm_h_st[(l + 1) & 1], bias, a));
+    if (n->tf32) {
+      lc.dynamicSmemBytes = ap::Mode<true>::kLayerSmem;
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<true>, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
+                                 n->tm_h_st[(l + 1) & 1], bias, a));
+    } else {
+      lc.dynamicSmemBytes = ap::Mode<false>::kLayerSmem;
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<false>, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
+                                 n->tm_h_st[(l + 1) & 1], bias, a));
+    }
   }
-  tail.bs = n->w.bs;
-  tail.bf = n->w.bf;
-  tail.wo = n->w.wo;
   tail.bo = n->w.bo;
+  tail.round_bias = n->round_bias;
   tail.B = Bc;
   tail.L = L;
   tail.tiles_per_clip = tiles_per_clip;
@@ -243,8 +255,13 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
   tail.num_layers = n->layers;
   {
     ProfSpan span(n, st, 1);
-    lc.dynamicSmemBytes = ap::Tc::kTailSmem;
-    AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel, n->tm_gate, n->tm_ws, n->tm_wf, tail));
+    if (n->tf32) {
+      lc.dynamicSmemBytes = ap::Mode<true>::kTailSmem;
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<true>, n->tm_gate, n->tm_ws, n->tm_wf, n->tail_bias, tail));
+    } else {
+      lc.dynamicSmemBytes = ap::Mode<false>::kTailSmem;
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<false>, n->tm_gate, n->tm_ws, n->tm_wf, n->tail_bias, tail));
+    }
   }
   AP_CUDA(cudaGetLastError());
   return 0;
@@ -318,6 +335,53 @@ int purify_loop(ap_net* n, const float* x_in, float* x_out, int B, int L, float 
   return 0;
 }
 
+int run_debug_gemm(bool tf32, const void* a, const void* b, float* d, int K, cudaStream_t st) {
+  const int subk = tf32 ? 32 : 64;
+  AP_CHECK(K > 0 && K % subk == 0, "K must be a positive multiple of one 128-byte operand row");
+  CUtensorMap ta, tb;
+  const uint64_t da[2] = {static_cast<uint64_t>(K), 128}, db[2] = {static_cast<uint64_t>(K), 256};
+  if (make_map(&ta, a, 2, da, 128, tf32) || make_map(&tb, b, 2, db, 256, tf32)) return 1;
+  const int smem = ap::kABytes + 256 * 128 + 64 + 1024;
+  if (tf32) {
+    AP_CUDA(cudaFuncSetAttribute(ap::debug_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ap::debug_gemm_kernel<true><<<1, 128, smem, st>>>(ta, tb, d, K);
+  } else {
+    AP_CUDA(cudaFuncSetAttribute(ap::debug_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ap::debug_gemm_kernel<false><<<1, 128, smem, st>>>(ta, tb, d, K);
+  }
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// How does tcgen05 kind::tf32 narrow an fp32 operand word?  1 + 0.75 ulp_tf32 times 1 comes back as 1 if the low 13
+// mantissa bits are dropped (then the kernels add half a tf32 ulp to every operand they write, which makes the
+// drop a round-to-nearest), as 1 + ulp if the tensor core rounds by itself (then they add nothing).
+int probe_tf32_round_bias(uint32_t* bias) {
+  float *a = nullptr, *b = nullptr, *d = nullptr;
+  const size_t na = 128 * 32, nb = 256 * 32, nd = 128 * 256;
+  AP_CUDA(cudaMalloc(&a, (na + nb + nd) * sizeof(float)));
+  b = a + na;
+  d = b + nb;
+  const float va = 1.0f + 0.75f / 1024.0f, vb = 1.0f;
+  float got = -1.f;
+  cudaError_t e = cudaMemset(a, 0, (na + nb + nd) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(a, &va, sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(b, &vb, sizeof(float), cudaMemcpyHostToDevice);
+  int rc = 0;
+  if (e == cudaSuccess) rc = run_debug_gemm(true, a, b, d, 32, nullptr);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpy(&got, d, sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(a);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(std::string("tf32 probe: ") + cudaGetErrorString(e));
+  if (got == 1.0f)
+    *bias = 0x1000u;
+  else if (got == 1.0f + 1.0f / 1024.0f)
+    *bias = 0u;
+  else
+    return fail("tf32 probe: unexpected product " + std::to_string(got));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -342,8 +406,16 @@ int ap_create(const ap_config* cfg, const ap_weights* w, ap_net** out) {
   n->layers = cfg->num_res_layers;
   n->cycle = cfg->dilation_cycle;
   n->T = cfg->T;
-  n->max_chunk = cfg->max_chunk > 0 ? cfg->max_chunk : 64;
-  AP_CHECK(cfg->flags == 0, "unknown ap_config.flags");
+  if ((cfg->flags & ~static_cast<uint32_t>(AP_FLAG_TF32)) != 0) {
+    delete n;
+    return fail("unknown ap_config.flags");
+  }
+  n->tf32 = (cfg->flags & AP_FLAG_TF32) != 0;
+  n->max_chunk = cfg->max_chunk > 0 ? cfg->max_chunk : (n->tf32 ? 32 : 64);
+  if (n->tf32 && probe_tf32_round_bias(&n->round_bias)) {
+    delete n;
+    return 1;
+  }
   n->w = *w;
   n->alpha.assign(cfg->alpha, cfg->alpha + cfg->T);
   n->alpha_bar.assign(cfg->alpha_bar, cfg->alpha_bar + cfg->T);
@@ -355,19 +427,24 @@ int ap_create(const ap_config* cfg, const ap_weights* w, ap_net** out) {
   const uint64_t L = static_cast<uint64_t>(n->layers);
   const uint64_t dw1[2] = {768, L * 512}, dw2[2] = {256, L * 256}, dws[2] = {L * 256, 256}, dwf[2] = {256, 256};
   const uint32_t brows = ap::Tc::kBRows;  // weight rows staged per CTA per K step (half of N = 256)
-  int rc = make_map(&n->tm_w1, w->w1, 2, dw1, brows) || make_map(&n->tm_w2, w->w2, 2, dw2, brows) ||
-           make_map(&n->tm_ws, w->ws, 2, dws, brows) || make_map(&n->tm_wf, w->wf, 2, dwf, brows);
+  int rc = make_map(&n->tm_w1, w->w1, 2, dw1, brows, n->tf32) || make_map(&n->tm_w2, w->w2, 2, dw2, brows, n->tf32) ||
+           make_map(&n->tm_ws, w->ws, 2, dws, brows, n->tf32) || make_map(&n->tm_wf, w->wf, 2, dwf, brows, n->tf32);
   if (rc) {
     delete n;
     return 1;
   }
   n->h_b1.resize(static_cast<size_t>(n->layers) * 512);
   n->h_c2.resize(static_cast<size_t>(n->T) * n->layers * ap::kC);
-  cudaError_t es[4] = {
+  cudaError_t es[] = {
       cudaMemcpy(n->h_b1.data(), w->b1, n->h_b1.size() * sizeof(float), cudaMemcpyDeviceToHost),
       cudaMemcpy(n->h_c2.data(), w->c2, n->h_c2.size() * sizeof(float), cudaMemcpyDeviceToHost),
-      cudaFuncSetAttribute(ap::layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc::kLayerSmem),
-      cudaFuncSetAttribute(ap::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Tc::kTailSmem)};
+      cudaMemcpy(n->tail_bias.bs, w->bs, sizeof(n->tail_bias.bs), cudaMemcpyDeviceToHost),
+      cudaMemcpy(n->tail_bias.bf, w->bf, sizeof(n->tail_bias.bf), cudaMemcpyDeviceToHost),
+      cudaMemcpy(n->tail_bias.wo, w->wo, sizeof(n->tail_bias.wo), cudaMemcpyDeviceToHost),
+      cudaFuncSetAttribute(ap::layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Mode<false>::kLayerSmem),
+      cudaFuncSetAttribute(ap::tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Mode<false>::kTailSmem),
+      cudaFuncSetAttribute(ap::layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Mode<true>::kLayerSmem),
+      cudaFuncSetAttribute(ap::tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ap::Mode<true>::kTailSmem)};
   for (cudaError_t e : es)
     if (e != cudaSuccess) {
       delete n;
@@ -569,14 +646,18 @@ int ap_profile_read(ap_net* net, double ms_sum[3], int64_t launches[3]) {
 
 int ap_debug_gemm(const void* a_bf16, const void* b_bf16, float* d, int K, void* stream) {
   AP_CHECK(a_bf16 && b_bf16 && d, "null tensor");
-  AP_CHECK(K > 0 && K % 64 == 0, "K must be a positive multiple of 64");
-  CUtensorMap ta, tb;
-  const uint64_t da[2] = {static_cast<uint64_t>(K), 128}, db[2] = {static_cast<uint64_t>(K), 256};
-  if (make_map(&ta, a_bf16, 2, da, 128) || make_map(&tb, b_bf16, 2, db, 256)) return 1;
-  const int smem = ap::kABytes + 256 * 128 + 64 + 1024;
-  AP_CUDA(cudaFuncSetAttribute(ap::debug_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  ap::debug_gemm_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, d, K);
-  AP_CUDA(cudaGetLastError());
+  return run_debug_gemm(false, a_bf16, b_bf16, d, K, static_cast<cudaStream_t>(stream));
+}
+
+int ap_debug_gemm_tf32(const float* a_f32, const float* b_f32, float* d, int K, void* stream) {
+  AP_CHECK(a_f32 && b_f32 && d, "null tensor");
+  return run_debug_gemm(true, a_f32, b_f32, d, K, static_cast<cudaStream_t>(stream));
+}
+
+int ap_precision(const ap_net* net, int* tf32, uint32_t* round_bias) {
+  AP_CHECK(net && tf32 && round_bias, "null argument");
+  *tf32 = net->tf32 ? 1 : 0;
+  *round_bias = net->round_bias;
   return 0;
 }
 

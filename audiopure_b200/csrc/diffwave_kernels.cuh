@@ -1,6 +1,7 @@
 // DiffWave epsilon-network kernels for sm_100a.
 //
 // Data layout in HBM:
+//   (bf16 build described; in the tf32 build the same tensors hold fp32 words, see Mode<>)
 //   h      : [B][L][256] bf16, channels-last -- a time step is one 512-byte row, so every conv tap of a
 //            128-step tile is one TMA box at row offset l0 + (tap-1)*dilation; the 3-D tensor map (c, l, b)
 //            zero-fills rows outside [0, L), which IS the conv's zero padding and keeps taps from bleeding
@@ -19,8 +20,7 @@ namespace ap {
 
 constexpr int kC = 256;          // residual / skip / gate channels (the only width the kernels support)
 constexpr int kTileT = 128;      // time steps per tile = UMMA M
-constexpr uint32_t kABytes = kTileT * 128;  // [128 rows x 64 bf16]: one K step of activations
-constexpr uint32_t kTileBytes = kTileT * kC * 2;  // a full [128 x 256] bf16 operand tile (4 swizzled sub-tiles)
+constexpr uint32_t kABytes = kTileT * 128;  // [128 rows x 128 bytes]: one K step of activations (64 bf16 / 32 tf32)
 constexpr int kThreads = 384;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warp 2: x loads (layer kernel), warp 3: idle, warps 4-11: epilogue
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiThreads = 256;
@@ -73,10 +73,11 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream_lo
 // K0: init conv (1 -> 256, k = 1, weight-norm folded) + ReLU + layer-0 step shift, fp32 [B][L] -> bf16
 // [B][L][256].  WaveNet.py:147,168 then :82-84 of block 0.  HBM-bound: 4 B in, 512 B out per time step.
 // ---------------------------------------------------------------------------------------------------
+template <bool kTf32>
 __global__ void __launch_bounds__(256) prologue_kernel(const float* __restrict__ x, const float* __restrict__ w0,
                                                        const float* __restrict__ b0,
                                                        const float* __restrict__ part0,
-                                                       __nv_bfloat16* __restrict__ h, long long rows) {
+                                                       void* __restrict__ h, long long rows, uint32_t round_bias) {
   const int cg = threadIdx.x & 31;  // this thread's 8 channels
   float w[8], b[8], p[8];
 #pragma unroll
@@ -89,15 +90,25 @@ __global__ void __launch_bounds__(256) prologue_kernel(const float* __restrict__
   for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
        row += stride) {
     const float xv = __ldg(x + row);
-    uint4 o;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    if constexpr (kTf32) {
+      uint4 o[2];
+      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float v0 = fmaxf(fmaf(w[2 * j], xv, b[2 * j]), 0.f) + p[2 * j];
-      const float v1 = fmaxf(fmaf(w[2 * j + 1], xv, b[2 * j + 1]), 0.f) + p[2 * j + 1];
-      ow[j] = pack_bf16x2(v0, v1);
+      for (int j = 0; j < 8; ++j) ow[j] = __float_as_uint(fmaxf(fmaf(w[j], xv, b[j]), 0.f) + p[j]) + round_bias;
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<float*>(h) + row * kC) + 2 * cg;
+      dst[0] = o[0];
+      dst[1] = o[1];
+    } else {
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v0 = fmaxf(fmaf(w[2 * j], xv, b[2 * j]), 0.f) + p[2 * j];
+        const float v1 = fmaxf(fmaf(w[2 * j + 1], xv, b[2 * j + 1]), 0.f) + p[2 * j + 1];
+        ow[j] = pack_bf16x2(v0, v1);
+      }
+      reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(h) + row * kC)[cg] = o;
     }
-    reinterpret_cast<uint4*>(h + row * kC)[cg] = o;
   }
 }
 
@@ -117,17 +128,86 @@ struct Tc {
   static constexpr uint32_t kBBytes = kBRows * 128;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kEpiWarps = kEpiThreads / 32;
-  static constexpr uint32_t kIdesc = umma_idesc_bf16(256, 256);
+};
+
+// The two precisions the tensor-core kernels are instantiated for.  bf16: operands bf16 in HBM and shared memory
+// (kind::f16).  tf32: operands are fp32 words (kind::tf32, the tensor core reads sign, exponent and 10 mantissa
+// bits); everything that is 64 bf16 wide in the bf16 build -- a 128-byte swizzled operand row, a TMA box, a K
+// step -- is 32 fp32 wide, so there are twice as many K steps and sub-tiles and the [128 x 256] operand tile is
+// 128 KB instead of 64 KB (which leaves room for a 3-stage ring only).
+template <bool kTf32>
+struct Mode : Tc {
+  static constexpr int kElem = kTf32 ? 4 : 2;
+  static constexpr int kSubK = 128 / kElem;         // channels per 128-byte operand row (one K step)
+  static constexpr int kSubs = kC / kSubK;          // [128 x kSubK] sub-tiles per 256 channels
+  static constexpr int kSubsPer64 = 64 / kSubK;     // sub-tiles per 64-channel epilogue chunk
+  static constexpr uint32_t kTileBytes = kTileT * kC * kElem;  // a full [128 x 256] operand tile
+  static constexpr uint32_t kIdesc = kTf32 ? umma_idesc_tf32(256, 256) : umma_idesc_bf16(256, 256);
   // TMA -> MMA ring depth.  The ring is latency-sensitive (3 -> 4 stages: -7 % layer, -11 % tail time), so
-  // everything else in shared memory is squeezed into ONE 64 KB operand tile per kernel to afford 5 stages.
+  // everything else in shared memory is squeezed into ONE operand tile per kernel to afford 5 stages (bf16).
 #ifndef AP_LAYER_STAGES
 #define AP_LAYER_STAGES 5
 #endif
-  static constexpr int kLayerStages = AP_LAYER_STAGES;
-  static constexpr int kTailStages = 4;
+  static constexpr int kLayerStages = kTf32 ? 3 : AP_LAYER_STAGES;
+  static constexpr int kTailStages = kTf32 ? 3 : 4;
   static constexpr uint32_t kLayerSmem = kLayerStages * kStageBytes + kTileBytes + 32 * 8 + 1024;
-  static constexpr uint32_t kTailSmem = kTailStages * kStageBytes + kTileBytes + 3 * 256 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 1024;
+  static constexpr uint32_t kTailSmem = kTailStages * kStageBytes + kTileBytes + 2 * 128 * 4 + 32 * 8 + 1024;
+  static_assert(kLayerStages <= 6 && kTailStages <= 4, "barrier slots");
+  static_assert(kLayerSmem <= 232448 && kTailSmem <= 232448, "over the 227 KB per-CTA shared-memory limit");
 };
+
+// 32 consecutive channels [32g, 32g+32) of time row `row` of a [128 x 256] K-major SW128 operand tile.
+// tf32: `round_bias` (0x1000 when the tensor core truncates the low 13 mantissa bits, see ap_create) is added to
+// the fp32 bit pattern on the way in, so that truncation rounds to nearest, and taken off again on the way out,
+// so the residual stream itself stays exact fp32.
+template <bool kTf32>
+__device__ __forceinline__ void tile_store32(uint8_t* tile, int row, int g, const float (&v)[32], uint32_t round_bias) {
+  if constexpr (kTf32) {
+    uint8_t* sub = tile + g * kABytes;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<uint4*>(sub + sw128_offset(row, c)) =
+          make_uint4(__float_as_uint(v[4 * c]) + round_bias, __float_as_uint(v[4 * c + 1]) + round_bias,
+                     __float_as_uint(v[4 * c + 2]) + round_bias, __float_as_uint(v[4 * c + 3]) + round_bias);
+  } else {
+    uint8_t* sub = tile + (g >> 1) * kABytes;
+    const int q0 = (g & 1) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(sub + sw128_offset(row, q0 + c)) =
+          make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                     pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+  }
+}
+template <bool kTf32>
+__device__ __forceinline__ void tile_load32(const uint8_t* tile, int row, int g, float (&v)[32], uint32_t round_bias) {
+  if constexpr (kTf32) {
+    const uint8_t* sub = tile + g * kABytes;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(sub + sw128_offset(row, c));
+      v[4 * c] = __uint_as_float(u.x - round_bias);
+      v[4 * c + 1] = __uint_as_float(u.y - round_bias);
+      v[4 * c + 2] = __uint_as_float(u.z - round_bias);
+      v[4 * c + 3] = __uint_as_float(u.w - round_bias);
+    }
+  } else {
+    const uint8_t* sub = tile + (g >> 1) * kABytes;
+    const int q0 = (g & 1) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(sub + sw128_offset(row, q0 + c));
+      v[8 * c] = bf16_lo(u.x);
+      v[8 * c + 1] = bf16_hi(u.x);
+      v[8 * c + 2] = bf16_lo(u.y);
+      v[8 * c + 3] = bf16_hi(u.y);
+      v[8 * c + 4] = bf16_lo(u.z);
+      v[8 * c + 5] = bf16_hi(u.z);
+      v[8 * c + 6] = bf16_lo(u.w);
+      v[8 * c + 7] = bf16_hi(u.w);
+    }
+  }
+}
 
 // Work distribution shared by all warp roles: unit u covers tiles 2u and 2u+1; this CTA takes tile 2u + rank.
 // A pair whose second tile does not exist gives that CTA an all-out-of-bounds tile (TMA zero-fills its loads
@@ -194,24 +274,27 @@ struct LayerArgs {
   int dilation, layer;
   int write_h;  // 0 for the last layer (its residual output is never consumed)
   int debug;    // ablation switches (AP_DEBUG env, profiles/r01_ablation.md): 2 no MUFU, 4 no h_next store, 8 no gate store
+  uint32_t round_bias;  // tf32 only: see tile_store32
 };
 struct LayerBias {  // passed by value: lives in the constant bank, read with warp-uniform indices
   float b1[512];    // conv bias, permuted like W1's rows
   float c2[256];    // sqrt(.5)*b_res + part_{n+1}(t)
 };
 
+template <bool kTf32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w1,
              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_gate_st,
              const __grid_constant__ CUtensorMap tm_h_st, const __grid_constant__ LayerBias bias,
              const LayerArgs a) {
-  using T = Tc;
+  using T = Mode<kTf32>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
   constexpr int kStages = T::kLayerStages;
+  constexpr int kSubs = T::kSubs, kSubK = T::kSubK;
   uint8_t* gate_s = smem + kStages * T::kStageBytes;  // the operand tile: gate, then x, then h_next
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gate_s + kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gate_s + T::kTileBytes);
   uint64_t* full = bars;             // [kStages] TMA -> MMA            (leader's copy is the live one)
   uint64_t* empty = bars + 6;        // [kStages] MMA -> TMA            (per CTA, multicast commit)
   uint64_t* d1_full = bars + 12;     // [2] chunk accumulator ready     MMA -> epilogue (per CTA)
@@ -219,8 +302,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   uint64_t* d2_full = bars + 16;     //     residual accumulator ready  MMA -> epilogue (per CTA)
   uint64_t* d2_empty = bars + 17;    //     residual accumulator drained epilogue -> MMA (leader)
   uint64_t* tile_free = bars + 18;   //     gate tile dead (GEMM2 + gate stores done)  epilogue -> x producer
-  uint64_t* x_full = bars + 19;      // [4] x sub-tile k landed in the operand tile    x producer -> epilogue
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
+  uint64_t* x_full = bars + 19;      // [kSubs <= 8] x sub-tile k landed in the operand tile    x producer -> epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -236,7 +319,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       mbar_init(&d1_full[s], 1);
       mbar_init(&gate_ready[s], 2 * T::kEpiWarps);
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&x_full[s], 1);
+    for (int s = 0; s < kSubs; ++s) mbar_init(&x_full[s], 1);
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, 2 * T::kEpiWarps);
     mbar_init(tile_free, T::kEpiWarps);
@@ -267,27 +350,27 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
       const uint32_t live = live_tap_mask(u, a.num_tiles, a.tiles_per_clip, a.dilation, a.L);
       for (int c = 0; c < 2; ++c) {
-        for (int ks = 0; ks < 12; ++ks) {
-          if (!((live >> (ks >> 2)) & 1)) continue;
+        for (int ks = 0; ks < 3 * kSubs; ++ks) {
+          const int tap = ks / kSubs;
+          if (!((live >> tap) & 1)) continue;
           const int s = it % kStages;
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 1);
           if (elect_one()) {
             mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
             uint8_t* sa = stage_base + s * T::kStageBytes;
-            const int tap = ks >> 2;
-            tma_load_3d_pair(sa, &tm_h, full0 + 8 * s, (ks & 3) * 64, tc.l0 + (tap - 1) * a.dilation, tc.b);
-            tma_load_2d_pair(sa + kABytes, &tm_w1, full0 + 8 * s, ks * 64, a.layer * 512 + c * 256 + brow);
+            tma_load_3d_pair(sa, &tm_h, full0 + 8 * s, (ks % kSubs) * kSubK, tc.l0 + (tap - 1) * a.dilation, tc.b);
+            tma_load_2d_pair(sa + kABytes, &tm_w1, full0 + 8 * s, ks * kSubK, a.layer * 512 + c * 256 + brow);
           }
           __syncwarp();
           ++it;
         }
       }
-      for (int ks = 0; ks < 4; ++ks, ++it) {
+      for (int ks = 0; ks < kSubs; ++ks, ++it) {
         const int s = it % kStages;
         mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 2);
         if (elect_one()) {
           mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kBBytes);
-          tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_w2, full0 + 8 * s, ks * 64,
+          tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_w2, full0 + 8 * s, ks * kSubK,
                            a.layer * 256 + brow);
         }
         __syncwarp();
@@ -304,7 +387,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         const uint32_t p = i & 1;
         const uint32_t bufA = tmem_base + (p ? 256u : 0u), bufB = tmem_base + (p ? 0u : 256u);
         const uint32_t live = live_tap_mask(u, a.num_tiles, a.tiles_per_clip, a.dilation, a.L);
-        const int last_ks = 4 * (31 - __clz(live)) + 3;  // the centre tap is live for any real tile
+        const int last_ks = kSubs * (31 - __clz(live)) + kSubs - 1;  // the centre tap is live for any real tile
         for (int c = 0; c < 2; ++c) {
           if (c == 1 && i > 0) {  // bufB held the previous tile's residual accumulator
             mbar_wait(d2_empty, (i - 1) & 1, 3);
@@ -312,8 +395,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
           }
           const uint32_t d = c ? bufB : bufA;
           uint32_t acc = 0;  // the first MMA issued into the buffer overwrites it
-          for (int ks = 0; ks < 12; ++ks) {
-            if (!((live >> (ks >> 2)) & 1)) continue;
+          for (int ks = 0; ks < 3 * kSubs; ++ks) {
+            if (!((live >> (ks / kSubs)) & 1)) continue;
             const int s = it % kStages;
             mbar_wait(&full[s], (it / kStages) & 1, 4);
             tc_fence_after();
@@ -321,7 +404,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
               const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
               const uint64_t db = da + static_cast<uint64_t>(kABytes >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, acc | k);
+              for (int k = 0; k < 4; ++k) umma_pair<kTf32>(d, da + 2 * k, db + 2 * k, T::kIdesc, acc | k);
               umma_commit_pair(&empty[s]);
               if (ks == last_ks) umma_commit_pair(&d1_full[c]);
             }
@@ -330,9 +413,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
             ++it;
           }
         }
-        for (int ks = 0; ks < 4; ++ks, ++it) {
-          if (ks == 0 || ks == 2) {  // K 0..127 needs gate half 0 (and bufA drained), K 128..255 half 1
-            mbar_wait(&gate_ready[ks >> 1], p, 5);
+        for (int ks = 0; ks < kSubs; ++ks, ++it) {
+          if (ks == 0 || ks == kSubs / 2) {  // K 0..127 needs gate half 0 (and bufA drained), K 128..255 half 1
+            mbar_wait(&gate_ready[ks ? 1 : 0], p, 5);
             tc_fence_after();
           }
           const int s = it % kStages;
@@ -342,9 +425,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
             const uint64_t da = gdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
             const uint64_t db = desc0 + static_cast<uint64_t>((s * T::kStageBytes + kABytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_pair(bufA, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_pair<kTf32>(bufA, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
             umma_commit_pair(&empty[s]);
-            if (ks == 3) umma_commit_pair(d2_full);
+            if (ks == kSubs - 1) umma_commit_pair(d2_full);
           }
           __syncwarp();
         }
@@ -353,25 +436,25 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   } else if (warp == 2) {
     // ======================= x producer: the layer input again, for the residual term ==================
     // Once the epilogue reports the gate tile dead (GEMM2 and the gate stores have read it), load the tile's
-    // own 128 input rows over it, one barrier per 64-channel sub-tile.
+    // own 128 input rows over it, one barrier per sub-tile.
     int i = 0;
     for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
       const TileCoord tc = tile_coord(2 * u + rank, a.num_tiles, a.tiles_per_clip);
       mbar_wait(tile_free, i & 1, 9);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kSubs; ++k) {
           mbar_arrive_expect_tx(&x_full[k], kABytes);
-          tma_load_3d(gate_s + k * kABytes, &tm_h, &x_full[k], k * 64, tc.l0, tc.b);
+          tma_load_3d(gate_s + k * kABytes, &tm_h, &x_full[k], k * kSubK, tc.l0, tc.b);
         }
       }
       __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
-    // ======================= epilogue (8 warps, each owns rows [32q,+32) of sub-tiles {hh, 2+hh}) ========
+    // ======================= epilogue (8 warps, each owns rows [32q,+32) of 64-channel chunks {hh, 2+hh}) ====
     const int e = warp - kEpiWarp0;
     const int q = warp & 3;   // TMEM lane quarter this warp may read
-    const int hh = e >> 2;    // warpgroup: which 64-channel sub-tiles / which half of a gate chunk
+    const int hh = e >> 2;    // warpgroup: which 64-channel chunks / which half of a gate chunk
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t gate_ready0 = mapa_u32(&gate_ready[0], 0);
@@ -392,7 +475,6 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         mbar_wait(&d1_full[c], p, 7);
         tc_fence_after();
         const uint32_t buf = (c ? bufB : bufA) + lane_addr;
-        uint8_t* sub = gate_s + (2 * c + hh) * kABytes;  // sub-tile of gate channels [128c + 64hh, +64)
 #pragma unroll
         for (int itn = 0; itn < 2; ++itn) {
           const int j0 = hh * 64 + itn * 32;  // gate channel within the chunk
@@ -402,36 +484,29 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
           tmem_ld_wait();
           const float* bt = bias.b1 + c * 256 + j0;
           const float* bs = bt + 128;
-          uint32_t pk[16];
+          float o[32];
           if (a.debug & 2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              pk[j] = pack_bf16x2(__uint_as_float(rt[2 * j]) + bt[2 * j] + __uint_as_float(rs[2 * j]) + bs[2 * j],
-                                  __uint_as_float(rt[2 * j + 1]) + bt[2 * j + 1] + __uint_as_float(rs[2 * j + 1]) +
-                                      bs[2 * j + 1]);
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(rt[j]) + bt[j] + __uint_as_float(rs[j]) + bs[j];
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float o0 = tanh_fast(__uint_as_float(rt[2 * j]) + bt[2 * j]) *
-                               sigmoid_fast(__uint_as_float(rs[2 * j]) + bs[2 * j]);
-              const float o1 = tanh_fast(__uint_as_float(rt[2 * j + 1]) + bt[2 * j + 1]) *
-                               sigmoid_fast(__uint_as_float(rs[2 * j + 1]) + bs[2 * j + 1]);
-              pk[j] = pack_bf16x2(o0, o1);
-            }
+            for (int j = 0; j < 32; ++j)
+              o[j] = gate_act<kTf32>(__uint_as_float(rt[j]) + bt[j], __uint_as_float(rs[j]) + bs[j]);
           }
-#pragma unroll
-          for (int v = 0; v < 4; ++v)
-            *reinterpret_cast<uint4*>(sub + sw128_offset(row, itn * 4 + v)) =
-                make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+          tile_store32<kTf32>(gate_s, row, 4 * c + 2 * hh + itn, o, a.round_bias);
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_cluster(gate_ready0 + 8 * c);
-          // this warp's [32 x 64] box of the gate tile -> HBM (operand of the tail's skip GEMM)
+          // this warp's [32 x 64-channel] part of the gate tile -> HBM (operand of the tail's skip GEMM)
           if (!(a.debug & 8)) {
-            tma_store_4d(&tm_gate_st, sub + q * 32 * 128, (2 * c + hh) * 64, l0 + q * 32, b, a.layer);
+#pragma unroll
+            for (int s = 0; s < T::kSubsPer64; ++s) {
+              const int sub = (2 * c + hh) * T::kSubsPer64 + s;
+              tma_store_4d(&tm_gate_st, gate_s + sub * kABytes + q * 32 * 128, sub * kSubK, l0 + q * 32, b, a.layer);
+            }
             tma_store_commit();
           }
         }
@@ -447,31 +522,22 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       __syncwarp();
 #pragma unroll 1
       for (int kk = 0; kk < 2; ++kk) {
-        const int k = hh + 2 * kk;  // 64-channel chunk == sub-tile index
-        uint8_t* sub = gate_s + k * kABytes;
+        const int k = hh + 2 * kk;  // 64-channel chunk
         uint32_t r0[32], r1[32];
         tmem_ld32(bufA + lane_addr + k * 64, r0);
         tmem_ld32(bufA + lane_addr + k * 64 + 32, r1);
-        mbar_wait(&x_full[k], p, 10);
-        tmem_ld_wait();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
+          const int g = 2 * k + half;  // 32-channel group
+          if (half == 0 || kTf32) mbar_wait(&x_full[g * 32 / kSubK], p, 10);
+          if (half == 0) tmem_ld_wait();
           const uint32_t* r = half ? r1 : r0;
-          uint4 xv[4];
+          const float* cc = bias.c2 + g * 32;
+          float v[32];
+          tile_load32<kTf32>(gate_s, row, g, v, a.round_bias);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) xv[v] = *reinterpret_cast<const uint4*>(sub + sw128_offset(row, half * 4 + v));
-          const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
-          const float* cc = bias.c2 + k * 64 + half * 32;
-          uint4 ov[4];
-          uint32_t* ow = reinterpret_cast<uint32_t*>(ov);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float v0 = fmaf(bf16_lo(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j]) + cc[2 * j]);
-            const float v1 = fmaf(bf16_hi(xw[j]), kSqrtHalf, __uint_as_float(r[2 * j + 1]) + cc[2 * j + 1]);
-            ow[j] = pack_bf16x2(v0, v1);
-          }
-#pragma unroll
-          for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(sub + sw128_offset(row, half * 4 + v)) = ov[v];
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], kSqrtHalf, __uint_as_float(r[j]) + cc[j]);
+          tile_store32<kTf32>(gate_s, row, g, v, a.round_bias);
         }
         if (kk == 1) {  // all of this warp's accumulator columns are in registers / consumed
           tc_fence_before();
@@ -484,7 +550,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       if (lane == 0 && a.write_h && !(a.debug & 4)) {
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk)
-          tma_store_3d(&tm_h_st, gate_s + (hh + 2 * kk) * kABytes + q * 32 * 128, (hh + 2 * kk) * 64, l0 + q * 32, b);
+#pragma unroll
+          for (int s = 0; s < T::kSubsPer64; ++s) {
+            const int sub = (hh + 2 * kk) * T::kSubsPer64 + s;
+            tma_store_3d(&tm_h_st, gate_s + sub * kABytes + q * 32 * 128, sub * kSubK, l0 + q * 32, b);
+          }
         tma_store_commit();
       }
     }
@@ -513,9 +583,6 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
 // tile i+1's K loop so the tensor pipe never waits for the epilogue.
 // ---------------------------------------------------------------------------------------------------
 struct TailArgs {
-  const float* bs;      // [256] sqrt(1/N) * sum_n b_skip,n
-  const float* bf;      // [256]
-  const float* wo;      // [256]
   float bo;
   const float* x_in;    // [B][L]
   const float* z;       // [B][L] injected noise or nullptr
@@ -526,27 +593,32 @@ struct TailArgs {
   uint32_t stream_lo;        // Philox stream: purpose/step id
   long long elem_offset;     // global element index of x_in[0] (keeps noise independent of sharding)
   int B, L, tiles_per_clip, num_tiles, num_layers;
+  uint32_t round_bias;       // tf32 only: see tile_store32
+};
+struct TailBias {  // passed by value: constant bank, warp-uniform indices
+  float bs[256];   // sqrt(1/N) * sum_n b_skip,n
+  float bf[256];   // final_conv[0] bias
+  float wo[256];   // final_conv[2] (256 -> 1) weight
 };
 
+template <bool kTf32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__ CUtensorMap tm_ws,
-            const __grid_constant__ CUtensorMap tm_wf, const TailArgs a) {
-  using T = Tc;
+            const __grid_constant__ CUtensorMap tm_wf, const __grid_constant__ TailBias bias, const TailArgs a) {
+  using T = Mode<kTf32>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* stage_base = smem;
   constexpr int kStages = T::kTailStages;
+  constexpr int kSubs = T::kSubs, kSubK = T::kSubK;
   uint8_t* s_tile = smem + kStages * T::kStageBytes;
-  float* bss = reinterpret_cast<float*>(s_tile + kTileBytes);
-  float* bfs = bss + 256;
-  float* wos = bfs + 256;
-  float* partial = wos + 256;  // [2 parities][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(partial + 512);
+  float* partial = reinterpret_cast<float*>(s_tile + T::kTileBytes);  // [2 parities][128 rows]: upper-half dot products
+  uint64_t* bars = reinterpret_cast<uint64_t*>(partial + 256);
   uint64_t* full = bars;           // [kStages]                        (leader)
   uint64_t* empty = bars + 4;      // [kStages]                        (per CTA)
   uint64_t* d_full = bars + 8;     // [2] skip accumulator ready       MMA -> epilogue (per CTA)
   uint64_t* d_empty = bars + 10;   // [2] buffer fully consumed        epilogue -> MMA (leader)
-  uint64_t* s_ready = bars + 12;   //     bf16 skip tile in smem       epilogue -> MMA (leader)
+  uint64_t* s_ready = bars + 12;   //     operand-precision skip tile in smem   epilogue -> MMA (leader)
   uint64_t* d3_full = bars + 13;   // [2] head accumulator ready       MMA -> epilogue (per CTA)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
@@ -555,11 +627,6 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   const int unit0 = static_cast<int>(blockIdx.x >> 1);
   const int units = static_cast<int>(gridDim.x >> 1);
 
-  for (int i = threadIdx.x; i < 256; i += kThreads) {
-    bss[i] = a.bs[i];
-    bfs[i] = a.bf[i];
-    wos[i] = a.wo[i];
-  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 2);
@@ -587,8 +654,8 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
   pdl_launch_dependents();
   pdl_wait();
 
-  const int total_ks = a.num_layers * 4;
-  const int J = total_ks / 2 < 16 ? total_ks / 2 : 16;  // where the previous tile's head GEMM is slotted in
+  const int total_ks = a.num_layers * kSubs;
+  const int J = total_ks / 2 < 4 * kSubs ? total_ks / 2 : 4 * kSubs;  // where the previous tile's head GEMM is slotted in
 
   if (warp == 0) {
     const uint32_t full0 = mapa_u32(&full[0], 0);
@@ -596,12 +663,12 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
     uint32_t it = 0;
     int i = 0;
     auto load_wf = [&]() {
-      for (int ks = 0; ks < 4; ++ks, ++it) {
+      for (int ks = 0; ks < kSubs; ++ks, ++it) {
         const int s = it % kStages;
         mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 11);
         if (elect_one()) {
           mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kBBytes);
-          tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_wf, full0 + 8 * s, ks * 64, brow);
+          tma_load_2d_pair(stage_base + s * T::kStageBytes + kABytes, &tm_wf, full0 + 8 * s, ks * kSubK, brow);
         }
         __syncwarp();
       }
@@ -615,8 +682,8 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         if (elect_one()) {
           mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
           uint8_t* sa = stage_base + s * T::kStageBytes;
-          tma_load_4d_pair(sa, &tm_gate, full0 + 8 * s, (ks & 3) * 64, tc.l0, tc.b, ks >> 2);
-          tma_load_2d_pair(sa + kABytes, &tm_ws, full0 + 8 * s, ks * 64, brow);
+          tma_load_4d_pair(sa, &tm_gate, full0 + 8 * s, (ks % kSubs) * kSubK, tc.l0, tc.b, ks / kSubs);
+          tma_load_2d_pair(sa + kABytes, &tm_ws, full0 + 8 * s, ks * kSubK, brow);
         }
         __syncwarp();
       }
@@ -632,7 +699,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         const uint32_t d = tmem_base + ((ip & 1) ? 256u : 0u);
         mbar_wait(s_ready, ip & 1, 13);
         tc_fence_after();
-        for (int ks = 0; ks < 4; ++ks, ++it) {
+        for (int ks = 0; ks < kSubs; ++ks, ++it) {
           const int s = it % kStages;
           mbar_wait(&full[s], (it / kStages) & 1, 14);
           tc_fence_after();
@@ -640,9 +707,9 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
             const uint64_t da = sdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
             const uint64_t db = desc0 + static_cast<uint64_t>((s * T::kStageBytes + kABytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_pair<kTf32>(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
             umma_commit_pair(&empty[s]);
-            if (ks == 3) umma_commit_pair(&d3_full[ip & 1]);
+            if (ks == kSubs - 1) umma_commit_pair(&d3_full[ip & 1]);
           }
           __syncwarp();
         }
@@ -663,7 +730,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
             const uint64_t da = desc0 + static_cast<uint64_t>((s * T::kStageBytes) >> 4);
             const uint64_t db = da + static_cast<uint64_t>(kABytes >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_pair(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_pair<kTf32>(d, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
             umma_commit_pair(&empty[s]);
             if (ks == total_ks - 1) umma_commit_pair(&d_full[p]);
           }
@@ -688,7 +755,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
       const uint32_t buf = tmem_base + (p ? 256u : 0u) + lane_addr;
       const bool row_ok = (l0 + row) < a.L;
 
-      // ---- skip sum -> bf16 operand tile ----
+      // ---- skip sum -> operand tile (bf16 / tf32) ----
       mbar_wait(&d_full[p], uu & 1, 17);
       tc_fence_after();
 #pragma unroll 1
@@ -697,17 +764,10 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         uint32_t r[32];
         tmem_ld32(buf + j0, r);
         tmem_ld_wait();
-        uint32_t pk[16];
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + bss[j0 + 2 * j],
-                              __uint_as_float(r[2 * j + 1]) + bss[j0 + 2 * j + 1]);
-        uint8_t* sub = s_tile + (j0 >> 6) * kABytes;
-        const int q0 = (j0 & 63) >> 3;
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          *reinterpret_cast<uint4*>(sub + sw128_offset(row, q0 + v)) =
-              make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias.bs[j0 + j];
+        tile_store32<kTf32>(s_tile, row, j0 >> 5, v, a.round_bias);
       }
       tc_fence_before();
       fence_proxy_async_smem();
@@ -725,15 +785,16 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         tmem_ld32(buf + j0, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc = fmaf(fmaxf(__uint_as_float(r[j]) + bfs[j0 + j], 0.f), wos[j0 + j], acc);
+        for (int j = 0; j < 32; ++j)
+          acc = fmaf(fmaxf(__uint_as_float(r[j]) + bias.bf[j0 + j], 0.f), bias.wo[j0 + j], acc);
       }
-      partial[(p * 2 + hh) * 128 + row] = acc;
+      if (hh == 1) partial[p * 128 + row] = acc;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(d_empty0 + 8 * p);
       named_bar_sync(1, kEpiThreads);
       if (hh == 0 && row_ok) {
-        const float eps = partial[(p * 2) * 128 + row] + partial[(p * 2 + 1) * 128 + row] + a.bo;
+        const float eps = acc + partial[p * 128 + row] + a.bo;
         const size_t idx = static_cast<size_t>(b) * a.L + l0 + row;
         if (a.eps_out) a.eps_out[idx] = eps;
         if (a.x_out) {
@@ -759,12 +820,15 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Bring-up / regression kernel: D[128 x 256] = A[128 x K] * B[256 x K]^T through exactly the TMA box,
+// Bring-up / regression kernel (also ap_create's probe of how the tensor core narrows fp32 operands to tf32):
+// D[128 x 256] = A[128 x K] * B[256 x K]^T through exactly the TMA box,
 // swizzle, descriptor and TMEM-load conventions the two kernels above rely on.  One CTA, 128 threads.
 // ---------------------------------------------------------------------------------------------------
+template <bool kTf32>
 __global__ void __launch_bounds__(128, 1)
 debug_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, float* d,
                   int K) {
+  constexpr int kSubK = Mode<kTf32>::kSubK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   constexpr uint32_t kStageBytes = kABytes + 256 * 128;
@@ -785,16 +849,20 @@ debug_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
-    for (int ks = 0; ks < K / 64; ++ks) {
+    constexpr uint32_t idesc = kTf32 ? umma_idesc_tf32(128, 256) : umma_idesc_bf16(128, 256);
+    for (int ks = 0; ks < K / kSubK; ++ks) {
       mbar_arrive_expect_tx(&bars[0], kStageBytes);
-      tma_load_2d(smem, &tm_a, &bars[0], ks * 64, 0);
-      tma_load_2d(smem + kABytes, &tm_b, &bars[0], ks * 64, 0);
+      tma_load_2d(smem, &tm_a, &bars[0], ks * kSubK, 0);
+      tma_load_2d(smem + kABytes, &tm_b, &bars[0], ks * kSubK, 0);
       mbar_wait(&bars[0], ks & 1, 21);
       tc_fence_after();
       const uint64_t da = umma_desc_sw128(smem_u32(smem)), db = umma_desc_sw128(smem_u32(smem + kABytes));
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_base, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (kTf32)
+          umma_tf32(tmem_base, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+        else
+          umma_bf16(tmem_base, umma_desc_advance_k(da, k), umma_desc_advance_k(db, k), idesc, (ks | k) != 0);
+      }
       umma_commit(&bars[1]);
       mbar_wait(&bars[1], ks & 1, 22);
     }

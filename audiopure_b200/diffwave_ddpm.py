@@ -115,14 +115,16 @@ class DiffWave(torch.nn.Module):
         return self.model.engine().one_shot(_as_tensor(x_t), self.reverse_timestep)
 
 
-def create_diffwave_model(model_path, config_path, reverse_timestep=25, device="cuda"):
-    """diffwave_ddpm.py:395-411.  ``model_path=None`` keeps the random init (no checkpoint offline)."""
+def create_diffwave_model(model_path, config_path, reverse_timestep=25, device="cuda", precision="bf16"):
+    """diffwave_ddpm.py:395-411.  ``model_path=None`` keeps the random init (no checkpoint offline).
+    ``precision``: "bf16" (default) or "tf32" -- the tensor-core mode of the residual-stack GEMMs."""
     with open(config_path) as f:
         cfg = json.loads(f.read())
     wavenet_config = cfg["wavenet_config"]
     diffusion_config = cfg["diffusion_config"]
     diffusion_hyperparams = calc_diffusion_hyperparams(**diffusion_config)
-    WaveNet_model = WaveNet_Speech_Commands(**wavenet_config, diffusion_config=diffusion_config).to(device)
+    WaveNet_model = WaveNet_Speech_Commands(**wavenet_config, diffusion_config=diffusion_config,
+                                            precision=precision).to(device)
     if model_path is not None:
         checkpoint = torch.load(model_path, map_location="cpu")
         WaveNet_model.load_state_dict(checkpoint["model_state_dict"])

@@ -93,7 +93,8 @@ class _PurifyWithLinearisedGrad(torch.autograd.Function):
 
 class RevDiffWave(torch.nn.Module):
     """diffwave_sde.py:138-218.  ``args`` carries the reference's attribute names: ``ddpm_path``, ``ddpm_config``,
-    ``t``, ``sample_step``, ``rand_t``, ``t_delta``, ``use_bm``, ``score_type``.  A ready ``DiffWave`` may be
+    ``t``, ``sample_step``, ``rand_t``, ``t_delta``, ``use_bm``, ``score_type`` (+ optional ``precision``:
+    "bf16" | "tf32").  A ready ``DiffWave`` may be
     passed as ``model=`` instead of a checkpoint path."""
 
     def __init__(self, args, device=None, model: DiffWave = None, seed: int = 0):
@@ -105,7 +106,8 @@ class RevDiffWave(torch.nn.Module):
         audio_shape = (1, 16000)
         if model is None:
             model = create_diffwave_model(model_path=args.ddpm_path, config_path=args.ddpm_config,
-                                          reverse_timestep=args.t, device=self.device)
+                                          reverse_timestep=args.t, device=self.device,
+                                          precision=getattr(args, "precision", "bf16"))
         model.eval().to(self.device)
         self.T = model.diffusion_hyperparams["T"]
         self.model = model

@@ -6,7 +6,7 @@ config: ``...conv.weight_g`` / ``...conv.weight_v`` / ``bias`` for the weight-no
 reference checkpoint loads with ``load_state_dict`` (``diffwave_ddpm.py:406-407``).  It holds no compute:
 ``forward`` hands the waveform to the sm_100a kernels through the C ABI.  Before the first evaluation
 (and after any ``load_state_dict``) the weights are packed once -- weight-norm folded, GEMM operands
-re-laid out and cast to bf16, the step-embedding MLP and every layer's ``fc_t`` tabulated for all T
+re-laid out and cast to bf16 (or rounded to tf32 with ``precision="tf32"``), the step-embedding MLP and every layer's ``fc_t`` tabulated for all T
 steps -- see ``pack_weights``.
 """
 
@@ -20,6 +20,14 @@ from . import _lib
 from .schedule import calc_diffusion_hyperparams, calc_diffusion_step_embedding, sde_tables
 
 DEFAULT_DIFFUSION_CONFIG = {"T": 200, "beta_0": 0.0001, "beta_T": 0.02}
+PRECISIONS = ("bf16", "tf32")
+
+
+def round_to_tf32(x):
+    """fp32 -> nearest tf32 (10 mantissa bits, ties away from zero), returned as fp32 words with the low 13 bits
+    clear: what the tensor core sees of an operand in the tf32 build (see ``tile_store32`` in csrc)."""
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 class _WNConv(nn.Module):
@@ -80,7 +88,7 @@ class WaveNet_Speech_Commands(nn.Module):
 
     def __init__(self, in_channels=1, res_channels=256, skip_channels=128, out_channels=1, num_res_layers=30,
                  dilation_cycle=10, diffusion_step_embed_dim_in=128, diffusion_step_embed_dim_mid=512,
-                 diffusion_step_embed_dim_out=512, diffusion_config=None, max_chunk=64):
+                 diffusion_step_embed_dim_out=512, diffusion_config=None, max_chunk=None, precision="bf16"):
         super().__init__()
         if not (in_channels == 1 and out_channels == 1 and res_channels == 256 and skip_channels == 256):
             raise NotImplementedError(
@@ -91,7 +99,10 @@ class WaveNet_Speech_Commands(nn.Module):
         self.dilation_cycle = dilation_cycle
         self.embed_dim_in = diffusion_step_embed_dim_in
         self.diffusion_config = dict(diffusion_config or DEFAULT_DIFFUSION_CONFIG)
-        self.max_chunk = max_chunk
+        if precision not in PRECISIONS:
+            raise NotImplementedError("precision must be one of %s, got %r" % (PRECISIONS, precision))
+        self.precision = precision      # "bf16" (default) or "tf32": include/audiopure_b200.h AP_FLAG_TF32
+        self.max_chunk = max_chunk or (32 if precision == "tf32" else 64)  # clips per pass (bounds the workspace)
         self.init_conv = nn.Sequential(_Wrap(_WNConv(in_channels, res_channels, 1)))
         self.residual_layer = _Group(res_channels, skip_channels, num_res_layers, diffusion_step_embed_dim_in,
                                      diffusion_step_embed_dim_mid, diffusion_step_embed_dim_out)
@@ -162,13 +173,17 @@ class WaveNet_Speech_Commands(nn.Module):
         w0, b0 = self.init_conv[0].conv.folded()
         wf, bf = self.final_conv[0].conv.folded()
         out = getattr(self.final_conv, "2").conv
+        if self.precision == "tf32":
+            op = lambda w: round_to_tf32(w.float())
+        else:
+            op = lambda w: w.to(torch.bfloat16).contiguous()
         packed = {
-            "w1": w1.to(torch.bfloat16).contiguous(), "b1": b1.contiguous(),
-            "w2": w2.to(torch.bfloat16).contiguous(), "c2": c2.contiguous(),
+            "w1": op(w1), "b1": b1.contiguous(),
+            "w2": op(w2), "c2": c2.contiguous(),
             "part0": part[:, 0, :].contiguous(),
             "w0": w0.to(dev)[:, 0, 0].contiguous(), "b0": b0.to(dev).contiguous(),
-            "ws": ws.to(torch.bfloat16).contiguous(), "bs": bs.contiguous(),
-            "wf": wf.to(dev)[:, :, 0].to(torch.bfloat16).contiguous(), "bf": bf.to(dev).contiguous(),
+            "ws": op(ws), "bs": bs.contiguous(),
+            "wf": op(wf.to(dev)[:, :, 0]), "bf": bf.to(dev).contiguous(),
             "wo": out.weight.detach().float().to(dev)[0, :, 0].contiguous(),
             "bo": float(out.bias.detach().float()[0]),
         }
@@ -211,8 +226,8 @@ class Engine:
         cfg.num_res_layers = model.num_res_layers
         cfg.dilation_cycle = model.dilation_cycle
         cfg.T = dc["T"]
-        cfg.max_chunk = model.max_chunk
-        cfg.flags = 0
+        cfg.max_chunk = int(model.max_chunk)
+        cfg.flags = _lib.AP_FLAG_TF32 if model.precision == "tf32" else 0
         for name, t in zip(("alpha", "alpha_bar", "sigma", "sde_beta", "sde_alphas_cumprod"), self._tables):
             setattr(cfg, name, ctypes.cast(t.data_ptr(), _lib.c_float_p))
         w = _lib.ApWeights()
@@ -229,6 +244,12 @@ class Engine:
                 self.lib.ap_destroy(self.handle)
         except Exception:
             pass
+
+    def precision(self):
+        """-> ("bf16"|"tf32", round_bias): what the handle runs and what ap_create's tf32 probe found."""
+        tf32, bias = ctypes.c_int(0), ctypes.c_uint32(0)
+        _lib.check(self.lib.ap_precision(self.handle, ctypes.byref(tf32), ctypes.byref(bias)))
+        return ("tf32" if tf32.value else "bf16"), bias.value
 
     def profile(self, enable):
         """Bracket every kernel launch with CUDA events (bench.py's roofline measurement)."""

@@ -25,10 +25,18 @@
 extern "C" {
 #endif
 
-#define AP_ABI_VERSION 3
+#define AP_ABI_VERSION 4
 
 typedef struct ap_net ap_net;   /* the packed DiffWave epsilon-network + its diffusion schedule */
 typedef struct ap_comm ap_comm; /* an NCCL communicator for the vote-count all-reduce           */
+
+/* Precision of the residual-stack GEMMs (north_star: "BF16 tensor-core mode" / "TF32 mode").  Default: bf16
+ * operands, fp32 accumulation, residual stream / gates / skip sum stored as bf16.  AP_FLAG_TF32: the same kernels
+ * instantiated for tcgen05 kind::tf32 -- the residual stream, gates and skip sum stay fp32 in HBM and shared
+ * memory, operands are rounded to tf32 (10 mantissa bits) only on their way into the tensor core, tanh/sigmoid are
+ * fp32-accurate.  About 2.2x slower and 2x the workspace; for parity work against the fp32 reference.
+ * With this flag the GEMM weights (w1, w2, ws, wf) are fp32 words already rounded to tf32.                    */
+#define AP_FLAG_TF32 1u
 
 /* configs/config.json "wavenet_config"/"diffusion_config" (diffwave_ddpm.py:395-402) + schedule tables.
  * The kernels support res_channels == skip_channels == 256, in/out channels == 1.               */
@@ -36,8 +44,8 @@ typedef struct ap_config {
   int32_t num_res_layers; /* 36 */
   int32_t dilation_cycle; /* 12 -> dilation 2^(n mod 12), WaveNet.py:116 */
   int32_t T;              /* 200 */
-  int32_t max_chunk;      /* clips processed per pass (bounds the workspace); 0 -> 64 */
-  uint32_t flags;         /* reserved, must be 0 */
+  int32_t max_chunk;      /* clips processed per pass (bounds the workspace); 0 -> 64 (bf16) / 32 (tf32) */
+  uint32_t flags;         /* 0 or AP_FLAG_TF32; any other bit is rejected */
   /* HOST pointers to fp32[T] tables, copied at create.  Built by the caller with the reference's own
    * expressions so they are bit-equal to it: util.py:111-123 and diffwave_sde.py:57-58.          */
   const float* alpha;
@@ -50,7 +58,7 @@ typedef struct ap_config {
 /* Packed weights, DEVICE pointers that must outlive the handle (WaveNet_Speech_Commands.pack_weights in audiopure_b200/wavenet.py builds them from
  * a reference-layout state dict: weight-norm folded once, WaveNet.py:28,67,72).                   */
 typedef struct ap_weights {
-  const void* w1;     /* bf16 [layers][512][768]: dilated conv, rows gate-interleaved, K = tap*256 + cin   */
+  const void* w1;     /* bf16 (fp32 with AP_FLAG_TF32, also w2/ws/wf) [layers][512][768]: dilated conv, rows gate-interleaved, K = tap*256 + cin   */
   const float* b1;    /* f32  [layers][512]: its bias, same row order                                      */
   const void* w2;     /* bf16 [layers][256][256]: sqrt(.5) * res_conv                                      */
   const float* c2;    /* f32  [T][layers][256]: sqrt(.5)*b_res[n] + fc_t[n+1](emb(t))  (0 shift for last)  */
@@ -151,8 +159,15 @@ void ap_comm_destroy(ap_comm* comm);
 int ap_profile_enable(ap_net* net, int enable);
 int ap_profile_read(ap_net* net, double ms_sum[3], int64_t launches[3]);
 
-/* Bring-up check of the tcgen05/TMA conventions: D[128][256] (f32) = A[128][K] * B[256][K]^T, bf16 inputs. */
+/* Bring-up check of the tcgen05/TMA conventions: D[128][256] (f32) = A[128][K] * B[256][K]^T, bf16 inputs
+ * (K a multiple of 64), or fp32 inputs through kind::tf32 (K a multiple of 32).                            */
 int ap_debug_gemm(const void* a_bf16, const void* b_bf16, float* d, int K, void* stream);
+int ap_debug_gemm_tf32(const float* a_f32, const float* b_f32, float* d, int K, void* stream);
+
+/* Which precision a handle was created with, and (tf32) what ap_create's probe found: round_bias is 0x1000 if the
+ * tensor core drops the low 13 mantissa bits of an fp32 operand (the kernels then pre-add half a tf32 ulp), 0 if
+ * it rounds to nearest itself.                                                                               */
+int ap_precision(const ap_net* net, int* tf32, uint32_t* round_bias);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,204 @@
+"""TF32 mode of the CUDA path (``precision="tf32"``, include/audiopure_b200.h AP_FLAG_TF32) against the oracle /
+golden fixtures.  Needs a B200.
+
+Tolerances (BASELINE.json north_star): purified waveform rel-L2 <= 1e-3 for TF32 mode; eps itself gated at 2e-3
+(SURVEY.md section 7 numerics).  The same kernels as the bf16 build, instantiated for fp32 storage and
+tcgen05 kind::tf32, so the structural tests (ragged tiles, dilation > L, chunking) are repeated here.
+"""
+
+import pytest
+import torch
+
+import audiopure_b200 as ap
+from audiopure_b200 import _lib
+from audiopure_b200.wavenet import round_to_tf32
+from oracle import purify as o_purify, schedule as o_schedule, wavenet as o_wavenet, weights as W
+from tests.emulate import emulate_eps_tf32
+
+pytestmark = pytest.mark.gpu
+
+EPS_GATE_TF32 = 2e-3
+WAVE_GATE_TF32 = 1e-3
+SMALL = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def make_model(cfg, seed, **kw):
+    m = ap.WaveNet_Speech_Commands(**cfg, precision="tf32", **kw)
+    m.load_state_dict(W.make_state_dict(seed, cfg))
+    return m.cuda().eval()
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    return make_model(W.DEFAULT_WAVENET_CONFIG, 1234)
+
+
+@pytest.fixture(scope="module")
+def small_model():
+    return make_model(SMALL, 99)
+
+
+@pytest.fixture(scope="module")
+def hp():
+    return ap.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+
+
+def _gemm_tf32(a, b):
+    lib = _lib.load()
+    d = torch.zeros(128, 256, device="cuda")
+    _lib.check(lib.ap_debug_gemm_tf32(a.data_ptr(), b.data_ptr(), d.data_ptr(), a.shape[1], _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return d.cpu()
+
+
+@pytest.mark.parametrize("K", [32, 256, 768])
+def test_debug_gemm_tf32(K):
+    """Operands already representable in tf32: how the tensor core narrows fp32 words does not matter, the result is
+    the fp32-accumulated product."""
+    g = torch.Generator().manual_seed(K)
+    a = round_to_tf32(torch.randn(128, K, generator=g))
+    b = round_to_tf32(torch.randn(256, K, generator=g))
+    want = a.double() @ b.double().t()
+    assert rel_l2(_gemm_tf32(a.cuda(), b.cuda()), want) < 1e-5
+
+
+def test_tf32_operand_narrowing_matches_the_probe(small_model):
+    """ap_create probes whether kind::tf32 drops or rounds the low 13 mantissa bits and sets the rounding bias the
+    kernels pre-add; check the probe's verdict against the hardware on a full operand, and that bias + hardware
+    together give round-to-nearest."""
+    mode, bias = small_model.engine().precision()
+    assert mode == "tf32" and bias in (0, 0x1000)
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(128, 64, generator=g)
+    b = round_to_tf32(torch.randn(256, 64, generator=g))
+    raw = _gemm_tf32(a.cuda(), b.cuda())
+    truncated = ((a.view(torch.int32) & ~0x1FFF).view(torch.float32)).double() @ b.double().t()
+    nearest = round_to_tf32(a).double() @ b.double().t()
+    if bias:
+        assert rel_l2(raw, truncated) < 1e-6
+    else:
+        assert rel_l2(raw, nearest) < 1e-4  # ties may differ (even vs away)
+    biased = (a.view(torch.int32) + bias).view(torch.float32)
+    assert rel_l2(_gemm_tf32(biased.cuda(), b.cuda()), nearest) < 1e-4
+
+
+def test_eps_small_ragged_vs_emulation_and_golden(small_model, golden):
+    g = golden("wavenet_small.npz")
+    t = int(g["t"])
+    x = W.make_waveforms(3, 1000, seed=int(g["x_seed"]))
+    got = small_model((x.cuda(), t * torch.ones(3, 1))).cpu()
+    packed = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in small_model.engine().packed.items()}
+    emu = emulate_eps_tf32(packed, x, t, 6, 3)
+    assert rel_l2(got, emu) < 2e-4           # same rounding points: accumulation order and rounding ties differ
+    assert rel_l2(got, g["eps"]) < EPS_GATE_TF32
+
+
+def test_layer_intermediates_vs_emulation(small_model):
+    """Every layer's gate tile and the final residual stream (read back from the workspace, rounding bias taken
+    off) against the emulation, clip edges and the ragged last tile included."""
+    x = W.make_waveforms(2, 1000, seed=11)
+    eng = small_model.engine()
+    _, bias = eng.precision()
+    eng.eps(x.cuda(), 3)
+    torch.cuda.synchronize()
+    B, L, layers = 2, 1000, 6
+    h_bytes = B * L * 256 * 4
+    ws = eng.workspace(B, L)
+    gate = ws[2 * h_bytes: 2 * h_bytes + layers * h_bytes].view(torch.int32) - bias
+    gate = gate.view(torch.float32).view(layers, B, L, 256).cpu()
+    packed = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in eng.packed.items()}
+    _, inter = emulate_eps_tf32(packed, x, 3, 6, 3, return_inter=True)
+    for n in range(layers):
+        err = rel_l2(gate[n], inter["gate"][n])
+        assert err < 1e-3, "layer %d gate rel-L2 %.3e" % (n, err)
+        edge = torch.cat([gate[n][:, :8], gate[n][:, -8:]], 1)
+        want = torch.cat([inter["gate"][n][:, :8], inter["gate"][n][:, -8:]], 1)
+        assert rel_l2(edge, want) < 2e-3, "layer %d clip edges" % n
+    # the residual stream written by layer 4 (input of the last layer; layer 5 writes none) lives in h[(4+1)&1]
+    h = (ws[h_bytes: 2 * h_bytes].view(torch.int32) - bias).view(torch.float32).view(B, L, 256).cpu()
+    assert rel_l2(h, inter["h"][4]) < 1e-4  # exact fp32 carrier: no operand rounding accumulates in it
+
+
+@pytest.mark.parametrize("t", [1, 33])
+def test_eps_full_vs_golden(full_model, golden, t):
+    g = golden("wavenet_full.npz")
+    x = W.make_waveforms(1, 16000, seed=0)
+    got = full_model.engine().eps(x.cuda(), t)
+    assert rel_l2(got, g["eps_t%d" % t]) < EPS_GATE_TF32
+
+
+def test_eps_is_batch_invariant_and_chunked(full_model):
+    """40 clips = one chunk of 32 + one of 8 (the tf32 default max_chunk is 32): each clip equals its own B = 1
+    evaluation bit for bit."""
+    x = W.make_waveforms(40, 16000, seed=2).cuda()
+    eng = full_model.engine()
+    big = eng.eps(x, 1)
+    for i in (0, 31, 32, 39):
+        assert torch.equal(big[i:i + 1], eng.eps(x[i:i + 1], 1)), i
+    assert torch.isfinite(big).all()
+
+
+@pytest.mark.parametrize("B,L", [(1, 129), (3, 77), (1, 128), (2, 4100)])
+def test_eps_odd_lengths(small_model, B, L):
+    sd = W.make_state_dict(99, SMALL)
+    x = W.make_waveforms(B, L, seed=L)
+    got = small_model.engine().eps(x.cuda(), 4)
+    assert rel_l2(got, o_wavenet.eps_theta(sd, x, 4, SMALL)) < EPS_GATE_TF32
+
+
+def test_eps_dilation_larger_than_clip():
+    cfg = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=13, dilation_cycle=12)
+    m = make_model(cfg, 5)
+    x = W.make_waveforms(2, 1500, seed=8)
+    got = m.engine().eps(x.cuda(), 9)
+    assert rel_l2(got, o_wavenet.eps_theta(W.make_state_dict(5, cfg), x, 9, cfg)) < EPS_GATE_TF32
+
+
+@pytest.mark.parametrize("t_star", [2, 3])
+def test_ddpm_purify_vs_reference(full_model, hp, golden, t_star):
+    g = golden("ddpm_t%d.npz" % t_star)
+    x = W.make_waveforms(2, 16000, seed=int(g["x_seed"]))
+    z = W.make_noise((t_star, 2, 1, 16000), seed=int(g["z_seed"]))
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=t_star)
+    assert rel_l2(dw(x.cuda(), z=z), g["purified"]) < WAVE_GATE_TF32
+
+
+def test_one_shot_vs_reference(full_model, hp, golden):
+    """The sensitive one: eps enters x0_hat scaled by sqrt(1/abar - 1) ~ 0.25 at t* = 34."""
+    g = golden("oneshot_t34.npz")
+    x = W.make_waveforms(1, 16000, seed=0)
+    dw = ap.DiffWave(full_model, hp, reverse_timestep=int(g["reverse_timestep"]))
+    assert rel_l2(dw.one_shot_denoise(x.cuda()), g["x0_hat"]) < WAVE_GATE_TF32
+
+
+def test_sde_purify_vs_oracle(small_model):
+    sd = W.make_state_dict(99, SMALL)
+    tab = o_schedule.sde_tables()
+    t = 3
+    x = W.make_waveforms(2, 2000, seed=3)
+    z = W.make_noise((t + 1, 2, 1, 2000), seed=9)
+    want = o_purify.sde_purify(tab, lambda xx, k: o_wavenet.eps_theta(sd, xx, k, SMALL), x, t, z[0],
+                               z[1:].reshape(t, 2, 2000))
+    got = small_model.engine().sde_purify(x.cuda(), t, z=z)
+    assert rel_l2(got, want) < WAVE_GATE_TF32
+
+
+def test_factory_precision(tmp_path):
+    import json
+    cfgp = tmp_path / "config.json"
+    cfgp.write_text(json.dumps({"wavenet_config": SMALL, "diffusion_config": W.DEFAULT_DIFFUSION_CONFIG}))
+    ckpt = tmp_path / "ckpt.pkl"
+    torch.save({"model_state_dict": W.make_state_dict(99, SMALL)}, ckpt)
+    dw = ap.create_diffwave_model(str(ckpt), str(cfgp), reverse_timestep=2, precision="tf32")
+    assert dw.model.engine().precision()[0] == "tf32"
+    dw16 = ap.create_diffwave_model(str(ckpt), str(cfgp), reverse_timestep=2)
+    assert dw16.model.engine().precision() == ("bf16", 0)
+    x = W.make_waveforms(1, 1024, seed=1).cuda()
+    ref = o_wavenet.eps_theta(W.make_state_dict(99, SMALL), x.cpu(), 3, SMALL)
+    assert rel_l2(dw.compute_eps_t(x, 3), ref) < rel_l2(dw16.compute_eps_t(x, 3), ref)

@@ -8,7 +8,7 @@ import torch
 
 import audiopure_b200 as ap
 from oracle import schedule as o_schedule, wavenet as o_wavenet, weights as W
-from tests.emulate import emulate_eps
+from tests.emulate import emulate_eps, emulate_eps_tf32
 
 SMALL = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
 
@@ -68,6 +68,34 @@ def test_packed_dataflow_bf16_within_gate():
     want = o_wavenet.eps_theta(sd, x, 7, SMALL)
     got = emulate_eps(packed, x, 7, 6, 3, quantize=True)
     assert rel_l2(got, want) < 2e-2
+
+
+def test_packed_dataflow_tf32_within_gate():
+    """The tf32 build (fp32 storage, operands rounded to 10 mantissa bits) keeps eps inside the 2e-3 gate."""
+    sd = W.make_state_dict(99, SMALL)
+    m = ap.WaveNet_Speech_Commands(**SMALL, precision="tf32")
+    m.load_state_dict(sd)
+    packed = m.pack_weights("cpu")
+    for k in ("w1", "w2", "ws", "wf"):
+        assert packed[k].dtype == torch.float32
+        assert int((packed[k].view(torch.int32) & 0x1FFF).abs().max()) == 0  # already tf32: low 13 bits clear
+    x = W.make_waveforms(2, 1000, seed=5)
+    want = o_wavenet.eps_theta(sd, x, 7, SMALL)
+    got = emulate_eps_tf32(packed, x, 7, 6, 3)
+    assert rel_l2(got, want) < 2e-3
+
+
+def test_round_to_tf32_is_nearest_with_ties_away():
+    from audiopure_b200.wavenet import round_to_tf32
+    u = 2.0 ** -10  # tf32 ulp at 1.0
+    x = torch.tensor([1.0, 1.0 + 0.25 * u, 1.0 + 0.5 * u, 1.0 + 0.75 * u, -1.0 - 0.5 * u, -1.0 - 0.49 * u, 0.0])
+    want = torch.tensor([1.0, 1.0, 1.0 + u, 1.0 + u, -1.0 - u, -1.0, 0.0])
+    assert torch.equal(round_to_tf32(x), want)
+
+
+def test_unknown_precision_is_rejected():
+    with pytest.raises(NotImplementedError):
+        ap.WaveNet_Speech_Commands(**SMALL, precision="fp8")
 
 
 def test_packing_is_refreshed_after_load_state_dict():

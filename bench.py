@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-sample-clips", type=int, default=1)
     ap.add_argument("--purifier", default="ddpm", choices=["ddpm", "sde"],
                     help="ddpm: DiffWave.forward (BASELINE configs[1], the headline); sde: RevDiffWave (configs[2])")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="tensor-core mode of the residual-stack GEMMs (the headline number is bf16)")
     ap.add_argument("--classifier", default="fused", choices=["fused", "module"],
                     help="consumer ResNeXt-29: bf16 channels-last with folded batch-norm, or the plain fp32 nn.Module")
     return ap.parse_args()
@@ -190,7 +192,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    model = ap.WaveNet_Speech_Commands(**S.DEFAULT_WAVENET_CONFIG)
+    model = ap.WaveNet_Speech_Commands(**S.DEFAULT_WAVENET_CONFIG, precision=args.precision)
     model.load_state_dict(S.diffwave_state_dict(1234))
     model = model.to(dev).eval()
     hp = ap.calc_diffusion_hyperparams(**S.DEFAULT_DIFFUSION_CONFIG)
@@ -260,13 +262,15 @@ def run_ours(args):
     evals_per_step = args.t_star * ((B + model.max_chunk - 1) // model.max_chunk)
     launches_per_step = (1 + evals_per_step * (model.num_res_layers + 2)) + ((B + model.max_chunk - 1) // model.max_chunk - 1) + 1
     peak, peak_src = measured_peak()
+    if args.precision == "tf32":  # no measured tf32 figure: the tensor core's tf32 rate is half its bf16 rate
+        peak, peak_src = peak / 2, peak_src + " / 2 (tf32 = half the bf16 rate)"
     clips_per_launch = min(B, model.max_chunk)
     achieved = clips_per_launch * LAYER_GFLOP_PER_CLIP / (layer_ms / max(layer_n, 1)) if layer_n else 0.0  # GFLOP/ms = TFLOP/s
 
     line = {
         "metric": "purified 1-s clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
         "clocks": clocks,
         "e2e": {"value": total_clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": B * CLIP_LEN * 4, "d2h_bytes_per_step": B * 8,
@@ -299,7 +303,7 @@ def run_ours(args):
                 "sample": "%d clip(s), DDPM t*=%d purify + log-mel + ResNeXt-29, fp32 oracle port, 1 warm-up + %d timed"
                           % (n, args.t_star, reps)}
         traffic_file = os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")
-        if os.path.exists(traffic_file):
+        if os.path.exists(traffic_file) and args.precision == "bf16":  # the ncu capture is of the bf16 kernel
             line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         print(json.dumps(line))
     if world > 1:

@@ -1,5 +1,5 @@
 """Bring-up diagnostics for the GPU box: each stage runs in its own process (a trapped kernel kills the
-CUDA context) and prints where parity breaks.  Usage: python tools/gpu_diag.py [stage ...]"""
+CUDA context) and prints where parity breaks.  Test infrastructure (it checks against oracle/), hence under tests/.  Usage: python tests/gpu_diag.py [stage ...]"""
 
 import json
 import os

@@ -48,6 +48,8 @@ def parse():
                     help="ddpm: DiffWave.forward (BASELINE configs[1], the headline); sde: RevDiffWave (configs[2])")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
                     help="tensor-core mode of the residual-stack GEMMs (the headline number is bf16)")
+    ap.add_argument("--no-same-box-peak", action="store_true",
+                    help="skip the ~3 s cuBLAS bf16 run that reports what THIS box sustains under its power cap")
     ap.add_argument("--classifier", default="fused", choices=["fused", "module"],
                     help="consumer ResNeXt-29: bf16 channels-last with folded batch-norm, or the plain fp32 nn.Module")
     return ap.parse_args()
@@ -288,6 +290,36 @@ def run_ours(args):
             "traffic": None,
         },
     }
+    if world == 1 and not args.no_same_box_peak:
+        # Supplementary evidence, not the roofline denominator: what cuBLAS bf16 (8192^3, back to back for ~3 s)
+        # sustains on THIS box right after the timed region, with its power draw -- the step is power-capped, and
+        # boxes differ in how many watts they allow.
+        n = 8192
+        a = torch.randn(n, n, device=dev, dtype=torch.bfloat16)
+        b = torch.randn(n, n, device=dev, dtype=torch.bfloat16)
+        for _ in range(5):
+            a @ b
+        torch.cuda.synchronize()
+        s2 = ClockSampler(local)
+        s2.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 0
+        t0 = time.perf_counter()
+        e0.record()
+        while time.perf_counter() - t0 < 3.0:
+            for _ in range(50):
+                a @ b
+            reps += 50
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        c2 = s2.stop()
+        tf = 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b
+        line["roofline"]["same_box_cublas"] = {
+            "tflops_sustained": tf, "sm_mhz": c2.get("sm_mhz"), "power_w_max": c2.get("power_w_max"),
+            "frac_of_it": achieved / tf if tf else None,
+            "how": "torch.matmul bf16 8192^3 back to back for 3 s on this GPU after the timed region"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             state = {}

@@ -80,6 +80,29 @@ class CifarResNeXt(nn.Module):
         return self.classifier(x.view(-1, self.stages[3]))
 
 
+def _bias_act(y, bias_f32, res=None, relu=True):
+    """y <- relu?(y + bias[c] (+ res)) in place.  bf16 channels-last CUDA activations take ONE pass through
+    ``ap_bias_act_nhwc_bf16`` (the bias add, residual add and clamp were 68 separate elementwise launches per batch);
+    anything else (fp32 / CPU, used by the tests of the folding) takes the torch ops."""
+    if (y.is_cuda and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+            and (res is None or (res.dtype == y.dtype and res.is_contiguous(memory_format=torch.channels_last)))):
+        from . import _lib
+        n, c, h, w = y.shape
+        with torch.cuda.device(y.device):
+            _lib.check(_lib.load().ap_bias_act_nhwc_bf16(y.data_ptr(), bias_f32.data_ptr(),
+                                                         res.data_ptr() if res is not None else None,
+                                                         n * h * w, c, 1 if relu else 0, _lib.stream_ptr()))
+        return y
+    y = y + bias_f32.to(y.dtype).reshape(1, -1, 1, 1)
+    if res is not None:
+        y = y + res
+    return F.relu(y, inplace=True) if relu else y
+
+
+def _conv_nobias(conv: nn.Conv2d, x):
+    return F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
 class _FusedBottleneck(nn.Module):
     def __init__(self, src: ResNeXtBottleneck):
         super().__init__()
@@ -87,15 +110,20 @@ class _FusedBottleneck(nn.Module):
         self.conv = _fold(src.conv_conv, src.bn)
         self.expand = _fold(src.conv_expand, src.bn_expand)
         self.shortcut = None
+        tail = self.expand.bias.detach().clone()
         if len(src.shortcut) > 0:
             self.shortcut = _fold(src.shortcut.shortcut_conv, src.shortcut.shortcut_bn)
+            tail = tail + self.shortcut.bias.detach()  # the two biases meet in the residual add: applied once
+        # fp32 bias tables for the fused epilogue (buffers: they stay fp32 when the convs are cast to bf16)
+        self.register_buffer("b_reduce", self.reduce.bias.detach().float().clone())
+        self.register_buffer("b_conv", self.conv.bias.detach().float().clone())
+        self.register_buffer("b_tail", tail.float())
 
     def forward(self, x):
-        y = F.relu(self.reduce(x), inplace=True)
-        y = F.relu(self.conv(y), inplace=True)
-        y = self.expand(y)
-        r = x if self.shortcut is None else self.shortcut(x)
-        return F.relu(r + y, inplace=True)
+        y = _bias_act(_conv_nobias(self.reduce, x), self.b_reduce)
+        y = _bias_act(_conv_nobias(self.conv, y), self.b_conv)
+        r = x if self.shortcut is None else _conv_nobias(self.shortcut, x)
+        return _bias_act(_conv_nobias(self.expand, y), self.b_tail, res=r)
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
@@ -112,7 +140,8 @@ class FusedResNeXt(nn.Module):
     """Inference form of a trained/loaded ``CifarResNeXt``: batch-norms folded into the
     convolutions, channels-last, bf16 weights and activations with fp32 accumulation (cuDNN), fp32 logits.
     ``FusedResNeXt(clf)`` is a drop-in for ``clf.eval()`` in the ``classifier`` slot; it removes the 31 batch-norm
-    and ~50 layout-conversion launches per batch that the reference module issues."""
+    and ~50 layout-conversion launches per batch that the reference module issues, and applies bias, residual add
+    and ReLU in one in-place pass per convolution (``ap_bias_act_nhwc_bf16``)."""
 
     def __init__(self, src: CifarResNeXt, dtype=torch.bfloat16):
         super().__init__()
@@ -122,14 +151,15 @@ class FusedResNeXt(nn.Module):
         self.blocks = nn.Sequential(*[_FusedBottleneck(b) for stage in (src.stage_1, src.stage_2, src.stage_3) for b in stage])
         self.classifier = src.classifier
         self.width = src.stages[3]
+        self.register_buffer("b_stem", self.stem.bias.detach().float().clone())
         self.to(memory_format=torch.channels_last)
-        self.stem.to(dtype)
-        self.blocks.to(dtype)
+        for conv in [m for m in self.modules() if isinstance(m, nn.Conv2d)]:
+            conv.to(dtype)  # the fp32 bias buffers of the fused epilogue are left alone
 
     @torch.no_grad()
     def forward(self, x):
         x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
-        x = F.relu(self.stem(x), inplace=True)
+        x = _bias_act(_conv_nobias(self.stem, x), self.b_stem)
         x = self.blocks(x)
         x = F.avg_pool2d(x, 8, 1).float()
         return self.classifier(x.reshape(-1, self.width))

@@ -623,6 +623,22 @@ int ap_vote_counts(const float* logits, int rows, int K, int64_t* counts, void* 
   return 0;
 }
 
+int ap_bias_act_nhwc_bf16(void* y, const float* bias, const void* residual, int64_t rows, int C, int relu,
+                          void* stream) {
+  AP_CHECK(y && bias, "null tensor");
+  AP_CHECK(rows > 0 && C > 0 && C % 8 == 0, "rows must be positive and C a positive multiple of 8");
+  AP_CHECK(reinterpret_cast<uintptr_t>(y) % 16 == 0 && reinterpret_cast<uintptr_t>(residual) % 16 == 0 &&
+               reinterpret_cast<uintptr_t>(bias) % 16 == 0,
+           "tensors must be 16-byte aligned");
+  const long long n_vec = static_cast<long long>(rows) * (C / 8);
+  long long blocks = (n_vec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ap::bias_act_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint4*>(y), bias, static_cast<const uint4*>(residual), n_vec, C / 8, relu);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int ap_profile_enable(ap_net* net, int enable) {
   AP_CHECK(net, "null handle");
   net->profile = enable != 0;

@@ -918,6 +918,37 @@ __global__ void __launch_bounds__(256) smooth_inputs_kernel(const float* __restr
   }
 }
 
+// Consumer-side epilogue (resnext.py:56-64 after batch-norm folding): y = relu?(y + bias[c] (+ res)) in
+// place over a channels-last bf16 activation [rows][C], 8 channels (16 bytes) per thread.  HBM/L2-bound: one
+// read-modify-write pass instead of torch's separate bias-add, residual-add and clamp passes.
+__global__ void __launch_bounds__(256) bias_act_kernel(uint4* __restrict__ y, const float* __restrict__ bias,
+                                                       const uint4* __restrict__ res, long long n_vec, int c_vec,
+                                                       int relu) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const int c0 = static_cast<int>(i % c_vec) * 8;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4 v = y[i];
+    uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (res) r = res[i];
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo = bf16_lo(vw[j]) + bb[2 * j] + bf16_lo(rw[j]);
+      float hi = bf16_hi(vw[j]) + bb[2 * j + 1] + bf16_hi(rw[j]);
+      if (relu) {
+        lo = fmaxf(lo, 0.f);
+        hi = fmaxf(hi, 0.f);
+      }
+      vw[j] = pack_bf16x2(lo, hi);
+    }
+    y[i] = v;
+  }
+}
+
 // certified_robust.py:58-67: counts[c] += #rows whose argmax is c (lowest index wins ties, like torch.max).
 __global__ void __launch_bounds__(256) vote_counts_kernel(const float* __restrict__ logits, int rows, int K,
                                                           unsigned long long* __restrict__ counts) {

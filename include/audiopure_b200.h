@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AP_ABI_VERSION 4
+#define AP_ABI_VERSION 5
 
 typedef struct ap_net ap_net;   /* the packed DiffWave epsilon-network + its diffusion schedule */
 typedef struct ap_comm ap_comm; /* an NCCL communicator for the vote-count all-reduce           */
@@ -143,6 +143,12 @@ int ap_smooth_inputs(const float* x, int L, int n_draws, float sigma, float scal
 /* certified_robust.py:58-67: counts[c] += #{rows : argmax_k logits[row][k] == c}; counts is int64[K] and
  * is accumulated into (zero it first).                                                                   */
 int ap_vote_counts(const float* logits, int rows, int K, int64_t* counts, void* stream);
+
+/* Consumer-side epilogue of the ResNeXt bottleneck after batch-norm folding (resnext.py:56-64):
+ *   y[r][c] = relu?(y[r][c] + bias[c] (+ residual[r][c]))      in place, y/residual channels-last bf16 [rows][C],
+ * bias f32[C], C a multiple of 8.  One pass instead of separate bias-add, residual-add and clamp launches.      */
+int ap_bias_act_nhwc_bf16(void* y, const float* bias, const void* residual, int64_t rows, int C, int relu,
+                          void* stream);
 
 /* Sharded certification: sum the int64 vote counts of all ranks (NCCL, loaded with dlopen).  The unique id
  * is created on rank 0 and handed to the other ranks by the caller (torch.distributed broadcast).        */

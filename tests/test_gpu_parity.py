@@ -425,6 +425,30 @@ def test_pipeline_agreement_on_a_batch_of_synthetic_clips(full_model, hp, classi
     assert float((got_logits.argmax(1).cpu() == want_logits.argmax(1)).float().mean()) >= 0.995
 
 
+@pytest.mark.parametrize("with_res,relu", [(False, True), (True, True), (True, False)])
+def test_bias_act_epilogue_kernel_bit_exact(with_res, relu):
+    """ap_bias_act_nhwc_bf16: y <- relu?(y + bias[c] (+ res)) in place over channels-last bf16, fp32 arithmetic, one
+    rounding -- bit-exact against the same expression in torch (ragged row count, C not a power of two)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    n, c, h, w = 3, 72, 5, 7
+    y = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    res = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, generator=g).cuda()
+    want = y.float() + bias.reshape(1, -1, 1, 1)
+    if with_res:
+        want = want + res.float()
+    if relu:
+        want = want.relu()
+    want = want.to(torch.bfloat16)
+    _lib.check(lib.ap_bias_act_nhwc_bf16(y.data_ptr(), bias.data_ptr(), res.data_ptr() if with_res else None,
+                                         n * h * w, c, int(relu), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(y, want)
+    with pytest.raises(_lib.AudioPureError):
+        _lib.check(lib.ap_bias_act_nhwc_bf16(y.data_ptr(), bias.data_ptr(), None, 10, 12, 1, _lib.stream_ptr()))
+
+
 def test_fused_bf16_classifier_agrees_with_fp32(classifier):
     """North star: classifier top-1 agreement >= 99.5 % on synthetic clips (bf16 fused consumer vs fp32 module)."""
     fused = ap.FusedResNeXt(classifier).cuda()

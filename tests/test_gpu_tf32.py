@@ -202,3 +202,37 @@ def test_factory_precision(tmp_path):
     x = W.make_waveforms(1, 1024, seed=1).cuda()
     ref = o_wavenet.eps_theta(W.make_state_dict(99, SMALL), x.cpu(), 3, SMALL)
     assert rel_l2(dw.compute_eps_t(x, 3), ref) < rel_l2(dw16.compute_eps_t(x, 3), ref)
+
+
+def test_top1_agreement_bf16_vs_tf32_on_512_clips(full_model, hp):
+    """north_star: classifier top-1 agreement >= 99.5 % on synthetic clips.  The CPU oracle is too slow for a sample
+    that resolves 0.5 %, so the wide check is between the two tensor-core modes (tf32 is within 3e-4 of the fp32
+    reference on eps): 512 clips, same Philox noise in both (it is keyed on seed / clip / sample, not on precision),
+    DDPM t*=2 -> log-mel -> ResNeXt-29 (fp32 module)."""
+    from oracle import resnext as o_resnext
+
+    clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
+    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    clf = clf.cuda().eval()
+    mel = ap.LogMelSpectrogram().cuda()
+    m16 = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
+    m16.load_state_dict(W.make_state_dict(1234))
+    m16 = m16.cuda().eval()
+    # clips of different loudness and spectra so that the random-init classifier does not answer one class for all
+    g = torch.Generator().manual_seed(11)
+    base = W.make_waveforms(512, 16000, seed=21)
+    tt = torch.arange(16000) / 16000.0
+    tone = torch.sin(2 * torch.pi * (100 + 3000 * torch.rand(512, 1, 1, generator=g)) * tt)
+    x = ((0.1 + 0.9 * torch.rand(512, 1, 1, generator=g)) * (0.5 * base + 0.5 * tone)).clamp(-1, 1).cuda()
+    outs = []
+    for model in (m16, full_model):
+        dw = ap.DiffWave(model, hp, reverse_timestep=2, seed=77)
+        with torch.no_grad():
+            y = dw(x)
+            outs.append((y, clf(mel(y))))
+    (y16, l16), (y32, l32) = outs
+    assert rel_l2(y16, y32) < 1e-4
+    agree = float((l16.argmax(1) == l32.argmax(1)).float().mean())
+    assert agree >= 0.995, agree
+    assert rel_l2(l16, l32) < 1e-2
+    assert len(torch.unique(l32.argmax(1))) > 1  # the check is not vacuous

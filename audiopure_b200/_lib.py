@@ -13,7 +13,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 c_i32_p = ctypes.POINTER(ctypes.c_int32)
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 
-AP_ABI_VERSION = 5
+AP_ABI_VERSION = 6
 AP_FLAG_TF32 = 1
 AP_COMM_ID_BYTES = 128
 
@@ -81,6 +81,10 @@ SIGNATURES = {
     "ap_logmel_backward": (_I, [_VP, _I, _I, _VP, _VP, ctypes.POINTER(ApMelTables), _VP]),
     "ap_smooth_inputs": (_I, [_VP, _I, _I, _F, _F, _VP, _U64, _U32, _I64, _VP, _VP]),
     "ap_vote_counts": (_I, [_VP, _I, _I, _VP, _VP]),
+    "ap_smooth_inputs_batch": (_I, [_VP, _I, _I, _I64, _I64, _I64, _F, _F, _VP, _U64, _U32, _VP, _VP]),
+    "ap_vote_counts_batch": (_I, [_VP, _I, _I, _I64, _I64, _I64, _I, _VP, _VP]),
+    "ap_nes_inputs": (_I, [_VP, _I, _I, _I, _I, _F, _VP, _U64, _U32, _I64, _VP, _VP]),
+    "ap_nes_grad": (_I, [_VP, _I, _I, _I, _I, _I, _F, _VP, _U64, _U32, _I64, _VP, _VP]),
     "ap_bias_act_nhwc_bf16": (_I, [_VP, _VP, _VP, _I64, _I, _I, _VP]),
     "ap_comm_unique_id": (_I, [ctypes.c_char_p]),
     "ap_comm_init": (_I, [_I, _I, ctypes.c_char_p, ctypes.POINTER(_VP)]),

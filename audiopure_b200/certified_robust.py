@@ -32,7 +32,8 @@ def shard_range(n, rank, world_size):
 
 class NcclCountsAllReduce:
     """Sums int64 device counters over ranks with ``ap_allreduce_counts``.  The NCCL unique id is created on
-    rank 0 and shipped through an already-initialised ``torch.distributed`` group (any backend)."""
+    rank 0 and shipped through an already-initialised ``torch.distributed`` group (any backend); a 1-rank
+    communicator needs no group."""
 
     def __init__(self, rank, world_size):
         import torch.distributed as dist
@@ -42,7 +43,8 @@ class NcclCountsAllReduce:
         if rank == 0:
             _lib.check(self.lib.ap_comm_unique_id(buf))
         box = [bytes(buf.raw)]
-        dist.broadcast_object_list(box, src=0)
+        if world_size > 1:
+            dist.broadcast_object_list(box, src=0)
         self.comm = ctypes.c_void_p()
         _lib.check(self.lib.ap_comm_init(rank, world_size, box[0], ctypes.byref(self.comm)))
 
@@ -68,17 +70,29 @@ def torch_counts_allreduce(counts):
 
 
 class RobustCertificate():
+    """``robustness_eval/certified_robust.py:6-127`` with the draw loop on the GPU.
+
+    Noise keys.  Every smoothing draw is Philox noise keyed on (``seed``, clip key, draw index).  Clip keys advance
+    with every call (a per-instance counter, like ``DiffWave._calls``): ``certify`` takes one fresh key per clip of
+    its batch, ``smooth_predict`` one per call, so successive dataloader batches -- and the selection (n_0) and
+    estimation (n) passes of one clip, which use disjoint draw indices -- never reuse a draw.  ``clip_offset=`` /
+    ``clip=`` / ``first_draw=`` override the keys (sharding tests, reproducing a certificate).  ``seed=None`` takes
+    ``torch.initial_seed()``: reseed torch (or pass ``seed``) to get different draws in another run.  With
+    ``world_size > 1`` every rank must be built with the same seed and make the same sequence of calls."""
 
     def __init__(self, classifier: torch.nn.Module, transform=None, denoiser=None, one_shot_rev: bool = False,
-                 num_classes=10, seed: int = 0, rank: int = 0, world_size: int = 1, allreduce=None):
+                 num_classes=10, seed: int = None, rank: int = 0, world_size: int = 1, allreduce=None):
         self.classifier = classifier
         self.transform = transform
         self.denoiser = denoiser
         self.num_classes = num_classes
         self.one_shot_rev = one_shot_rev
-        self.seed = seed
+        self.seed = (torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self.rank, self.world_size = rank, world_size
         self.allreduce = allreduce
+        self._next_clip_key = 0
+        self._x_in = None
+        self.last_counts = None  # (counts_0, counts) of the last certify call, int64 CPU tensors [clips][classes]
         if world_size > 1 and allreduce is None:
             raise ValueError("world_size > 1 needs an allreduce callable (NcclCountsAllReduce or torch_counts_allreduce)")
 
@@ -92,59 +106,85 @@ class RobustCertificate():
             x_in = self.transform(x_in)
         return self.classifier(x_in)
 
-    @torch.no_grad()
-    def smooth_predict(self, x: torch.Tensor, num_sampling: int = 100, sigma=0.25, batch_size=64, z: torch.Tensor = None,
-                       clip: int = 0, first_draw: int = 0):
-        """certified_robust.py:33-67 -> int64 counts[num_classes] (CPU tensor, like the reference).
+    def _take_clip_keys(self, n, override):
+        if override is not None:
+            return int(override)
+        key = self._next_clip_key
+        self._next_clip_key += n
+        return key
 
-        ``z``: optional injected standard-normal draws (num_sampling, 1, L); ``clip`` / ``first_draw`` key the
-        Philox stream so that every (clip, draw) pair has its own noise whatever the sharding or batching."""
-        assert (x.shape[0] == 1)
+    def _scale_for(self, sigma):
+        """certified_robust.py:50-54: retarget the denoiser to t*(sigma) and return sqrt(alpha_bar*)."""
+        if self.denoiser is None:
+            return 1.0
+        alpha_bar_star = 1 / (1 + sigma ** 2)
+        self.denoiser.reverse_timestep = self.compute_t_star(alpha_bar_star)
+        return alpha_bar_star ** 0.5
+
+    def _count_votes(self, x, per_clip, n_split, first_draw, sigma, batch_size, z, clip_key0):
+        """Votes of every (clip, draw) pair, draw in [0, per_clip), of the clips ``x`` (C, L): the clip-major work
+        list is cut into this rank's contiguous slice and then into FULL batches that may span clips, so neither a
+        small n_0 nor many ranks leaves the GPU with a sliver of a batch.  Returns int64 device counts [2][C][K]
+        (draws < n_split | draws >= n_split), summed over ranks with ONE all-reduce."""
         lib = _lib.load()
         if not x.is_cuda:
-            raise _lib.AudioPureError("smooth_predict runs on a CUDA device only (no CPU fallback)")
-        x = x.to(torch.float32).contiguous()
-        L = x.shape[-1]
-        lo, hi = shard_range(num_sampling, self.rank, self.world_size)
-        scale = 1.0
-        if self.denoiser is not None:
-            alpha_bar_star = 1 / (1 + sigma ** 2)
-            t_star = self.compute_t_star(alpha_bar_star)
-            self.denoiser.reverse_timestep = t_star
-            scale = alpha_bar_star ** 0.5
-        counts = torch.zeros(self.num_classes, dtype=torch.int64, device=x.device)
+            raise _lib.AudioPureError("smooth_predict / certify run on a CUDA device only (no CPU fallback)")
+        C, L = x.shape
+        K = self.num_classes
+        scale = self._scale_for(sigma)
+        counts = torch.zeros(2, C, K, dtype=torch.int64, device=x.device)
         if z is not None:
             z = z.to(device=x.device, dtype=torch.float32).contiguous()
-            assert z.shape[0] == num_sampling and z.shape[-1] == L
+            assert z.numel() == C * per_clip * L, "injected noise must be (clips, draws, 1, L)"
+        lo, hi = shard_range(C * per_clip, self.rank, self.world_size)
+        if self._x_in is None or self._x_in.shape != (batch_size, 1, L) or self._x_in.device != x.device:
+            self._x_in = torch.empty(batch_size, 1, L, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             for s in range(lo, hi, batch_size):
                 b = min(batch_size, hi - s)
-                x_in = torch.empty(b, 1, L, dtype=torch.float32, device=x.device)
-                zb = z[s:s + b] if z is not None else None
-                _lib.check(lib.ap_smooth_inputs(x.data_ptr(), L, b, float(sigma), float(scale),
-                                                zb.data_ptr() if zb is not None else None, self.seed, clip,
-                                                first_draw + s, x_in.data_ptr(), _lib.stream_ptr()))
+                x_in = self._x_in[:b]
+                _lib.check(lib.ap_smooth_inputs_batch(x.data_ptr(), L, b, s, per_clip, first_draw, float(sigma),
+                                                      float(scale), z.data_ptr() if z is not None else None,
+                                                      self.seed, clip_key0, x_in.data_ptr(), _lib.stream_ptr()))
                 logits = self.forward(x_in).to(torch.float32).contiguous()
-                assert logits.shape[-1] == self.num_classes
-                _lib.check(lib.ap_vote_counts(logits.data_ptr(), b, self.num_classes, counts.data_ptr(),
-                                              _lib.stream_ptr()))
-            if self.world_size > 1:
+                assert logits.shape == (b, K)
+                _lib.check(lib.ap_vote_counts_batch(logits.data_ptr(), b, K, s, per_clip, n_split, C,
+                                                    counts.data_ptr(), _lib.stream_ptr()))
+            if self.allreduce is not None:
                 self.allreduce(counts)
-        return counts.cpu()
+        return counts
+
+    @torch.no_grad()
+    def smooth_predict(self, x: torch.Tensor, num_sampling: int = 100, sigma=0.25, batch_size=64, z: torch.Tensor = None,
+                       clip: int = None, first_draw: int = 0):
+        """certified_robust.py:33-67 -> int64 counts[num_classes] (CPU tensor, like the reference).
+
+        ``z``: optional injected standard-normal draws (num_sampling, 1, L).  ``clip`` / ``first_draw`` override the
+        Philox key of this call (default: a fresh clip key per call, draws 0..num_sampling-1)."""
+        assert (x.shape[0] == 1)
+        x = x.to(torch.float32).reshape(1, -1).contiguous()
+        counts = self._count_votes(x, num_sampling, num_sampling, first_draw, sigma, batch_size, z,
+                                   self._take_clip_keys(1, clip))
+        return counts[0, 0].cpu()
 
     @torch.no_grad()
     def certify(self, x: torch.Tensor, y: torch.Tensor, sigma: float = 0.25, n_0: int = 100, n: int = 100000,
-                alpha: float = 0.001, batch_size: int = 64, clip_offset: int = 0):
-        """certified_robust.py:69-100 -> (y_pred, radius)."""
+                alpha: float = 0.001, batch_size: int = 64, clip_offset: int = None, z: torch.Tensor = None):
+        """certified_robust.py:69-100 -> (y_pred, radius).
+
+        All clips of the call go through ONE work list: draws [0, n_0) of a clip are its selection pass
+        (:84-87), draws [n_0, n_0 + n) its estimation pass (:89-93); the votes are counted on the device, summed
+        over ranks once and read back once, then the Clopper-Pearson bound and the radius (:94-100) are evaluated
+        on the host in float64 like the reference.  ``z``: optional injected draws (clips, n_0 + n, 1, L)."""
+        C = x.shape[0]
+        xs = x.to(torch.float32).reshape(C, -1).contiguous()
+        counts = self._count_votes(xs, n_0 + n, n_0, 0, sigma, batch_size, z, self._take_clip_keys(C, clip_offset)).cpu()
+        counts_0, counts_n = counts[0], counts[1]
+        self.last_counts = (counts_0, counts_n)
         y_pred, radius = -torch.ones_like(y), torch.zeros_like(y, dtype=torch.float32)
-        for i in range(x.shape[0]):
-            x_in = x[i]
-            counts_0 = self.smooth_predict(x_in, num_sampling=n_0, sigma=sigma, batch_size=batch_size,
-                                           clip=clip_offset + i, first_draw=0)
-            c_A = counts_0.max(0, keepdim=True)[1].item()
-            counts = self.smooth_predict(x_in, num_sampling=n, sigma=sigma, batch_size=batch_size,
-                                         clip=clip_offset + i, first_draw=n_0)
-            pa = self.lower_conf_bound(k=counts[c_A], n=n, alpha=alpha)
+        for i in range(C):
+            c_A = counts_0[i].max(0, keepdim=True)[1].item()
+            pa = self.lower_conf_bound(k=counts_n[i, c_A], n=n, alpha=alpha)
             if pa > 0.5:
                 y_pred[i] = c_A
                 radius[i] = sigma * norm.ppf(pa)

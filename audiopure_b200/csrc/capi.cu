@@ -78,6 +78,27 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, u
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// SM count of the current device (the grid-stride kernels are sized in multiples of it), cached per device.
+int current_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// Blocks for a grid-stride kernel over n items: enough to cover them, at most ctas_per_sm per SM.
+unsigned grid_for(long long n, int threads, int ctas_per_sm) {
+  long long blocks = (n + threads - 1) / threads;
+  const long long cap = static_cast<long long>(current_sm_count()) * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  return static_cast<unsigned>(blocks < 1 ? 1 : blocks);
+}
+
 }  // namespace
 
 struct ap_net {
@@ -599,26 +620,104 @@ int ap_logmel_backward(const float* x, int B, int L, const float* grad_out, floa
   return 0;
 }
 
+int ap_smooth_inputs_batch(const float* x, int L, int n_rows, int64_t flat0, int64_t per_clip, int64_t first_draw,
+                           float sigma, float scale, const float* z, uint64_t seed, uint32_t clip_key0, float* out,
+                           void* stream) {
+  AP_CHECK(x && out, "null tensor");
+  AP_CHECK(L > 0 && n_rows > 0, "L and n_rows must be positive");
+  AP_CHECK(flat0 >= 0 && per_clip > 0 && first_draw >= 0, "flat0 / first_draw must be >= 0 and per_clip positive");
+  ap::SmoothArgs a;
+  a.x = x;
+  a.zinj = z;
+  a.out = out;
+  a.L = L;
+  a.n_rows = n_rows;
+  a.flat0 = flat0;
+  a.per_clip = per_clip;
+  a.first_draw = first_draw;
+  a.sigma = sigma;
+  a.scale = scale;
+  a.seed = seed;
+  a.clip_key0 = clip_key0;
+  const bool vec = (L % 4 == 0) && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(z) % 16 == 0;
+  if (!vec && L % 4 == 0) return fail("ap_smooth_inputs: tensors must be 16-byte aligned when L is a multiple of 4");
+  const long long n = static_cast<long long>(n_rows) * (vec ? L / 4 : L);
+  ap::smooth_inputs_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int ap_smooth_inputs(const float* x, int L, int n_draws, float sigma, float scale, const float* z, uint64_t seed,
                      uint32_t clip, int64_t first_draw, float* out, void* stream) {
-  AP_CHECK(x && out, "null tensor");
-  AP_CHECK(L > 0 && n_draws > 0, "L and n_draws must be positive");
-  const long long n = static_cast<long long>(n_draws) * L;
-  long long blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  ap::smooth_inputs_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, z, out, L, n_draws, sigma, scale, seed, clip, first_draw);
+  // one clip: the work list is just its draws (per_clip larger than any draw count keeps clip == 0)
+  return ap_smooth_inputs_batch(x, L, n_draws, 0, int64_t(1) << 62, first_draw, sigma, scale, z, seed, clip, out, stream);
+}
+
+int ap_vote_counts_batch(const float* logits, int rows, int K, int64_t flat0, int64_t per_clip, int64_t n_split,
+                         int n_clips, int64_t* counts, void* stream) {
+  AP_CHECK(logits && counts, "null tensor");
+  AP_CHECK(rows > 0 && K > 0 && n_clips > 0, "rows, K and n_clips must be positive");
+  AP_CHECK(flat0 >= 0 && per_clip > 0, "flat0 must be >= 0 and per_clip positive");
+  AP_CHECK((flat0 + rows - 1) / per_clip < n_clips, "rows reach past the last clip's counters");
+  ap::vote_counts_kernel<<<grid_for(rows, 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, rows, K, flat0, per_clip, n_split, n_clips, reinterpret_cast<unsigned long long*>(counts));
   AP_CUDA(cudaGetLastError());
   return 0;
 }
 
 int ap_vote_counts(const float* logits, int rows, int K, int64_t* counts, void* stream) {
-  AP_CHECK(logits && counts, "null tensor");
-  AP_CHECK(rows > 0 && K > 0, "rows and K must be positive");
-  int blocks = (rows + 255) / 256;
-  if (blocks > 148) blocks = 148;
-  ap::vote_counts_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, rows, K, reinterpret_cast<unsigned long long*>(counts));
+  return ap_vote_counts_batch(logits, rows, K, 0, int64_t(1) << 62, int64_t(1) << 62, 1, counts, stream);
+}
+
+namespace {
+int nes_args(ap::NesArgs* a, const float* x, int audios, int L, int S, int lead, float sigma, const float* z,
+             uint64_t seed, uint32_t audio_key0, int64_t draw0) {
+  AP_CHECK(x, "null tensor");
+  AP_CHECK(audios > 0 && L > 0, "audios and L must be positive");
+  AP_CHECK(S > 0 && S % 2 == 0, "samples per draw batch must be positive and even (antithetic pairs, _NES.py:19-21)");
+  AP_CHECK(lead == 0 || lead == 1, "lead must be 0 or 1");
+  AP_CHECK(draw0 >= 0, "draw0 must be >= 0");
+  *a = ap::NesArgs{};
+  a->x = x;
+  a->zinj = z;
+  a->L = L;
+  a->audios = audios;
+  a->S = S;
+  a->lead = lead;
+  a->sigma = sigma;
+  a->seed = seed;
+  a->audio_key0 = audio_key0;
+  a->draw0 = draw0;
+  return 0;
+}
+}  // namespace
+
+int ap_nes_inputs(const float* x, int audios, int L, int S, int lead, float sigma, const float* z, uint64_t seed,
+                  uint32_t audio_key0, int64_t draw0, float* out, void* stream) {
+  ap::NesArgs a;
+  if (nes_args(&a, x, audios, L, S, lead, sigma, z, seed, audio_key0, draw0)) return 1;
+  AP_CHECK(out, "null tensor");
+  a.out = out;
+  const long long n = static_cast<long long>(audios) * (S / 2) * L;
+  ap::nes_inputs_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  AP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ap_nes_grad(const float* loss, int loss_stride, int loss_off, int audios, int L, int S, float grad_scale,
+                const float* z, uint64_t seed, uint32_t audio_key0, int64_t draw0, float* grad, void* stream) {
+  ap::NesArgs a;
+  if (nes_args(&a, loss, audios, L, S, 0, 0.f, z, seed, audio_key0, draw0)) return 1;
+  AP_CHECK(grad, "null tensor");
+  AP_CHECK(loss_off >= 0 && loss_off + S <= loss_stride, "loss row too short for S samples at loss_off");
+  a.loss = loss;
+  a.loss_stride = loss_stride;
+  a.loss_off = loss_off;
+  a.grad = grad;
+  a.grad_scale = grad_scale;
+  const long long n = static_cast<long long>(audios) * L;
+  ap::nes_grad_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   AP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -631,9 +730,7 @@ int ap_bias_act_nhwc_bf16(void* y, const float* bias, const void* residual, int6
                reinterpret_cast<uintptr_t>(bias) % 16 == 0,
            "tensors must be 16-byte aligned");
   const long long n_vec = static_cast<long long>(rows) * (C / 8);
-  long long blocks = (n_vec + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  ap::bias_act_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ap::bias_act_kernel<<<grid_for(n_vec, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<uint4*>(y), bias, static_cast<const uint4*>(residual), n_vec, C / 8, relu);
   AP_CUDA(cudaGetLastError());
   return 0;

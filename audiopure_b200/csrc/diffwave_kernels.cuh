@@ -69,6 +69,25 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream_lo
   return rad * ((sel & 1) ? s : c);
 }
 
+// The four normals of Philox block `blk` (elements 4*blk .. 4*blk+3 of the stream): the same values philox_normal
+// returns one at a time, for kernels that walk a row in float4 steps.
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t stream_lo, uint32_t stream_hi, uint64_t blk,
+                                               float (&out)[4]) {
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), stream_lo, stream_hi,
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = (static_cast<float>(r[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = static_cast<float>(r[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    out[2 * h] = rad * cs;
+    out[2 * h + 1] = rad * sn;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K0: init conv (1 -> 256, k = 1, weight-norm folded) + ReLU + layer-0 step shift, fp32 [B][L] -> bf16
 // [B][L][256].  WaveNet.py:147,168 then :82-84 of block 0.  HBM-bound: 4 B in, 512 B out per time step.
@@ -900,21 +919,124 @@ __global__ void __launch_bounds__(256) axpbz_kernel(const float* __restrict__ x,
   }
 }
 
-// Smoothing draws (certified_robust.py:46-54): out[j][l] = scale * (x[l] + sigma * z_j[l]) for draws
-// j in [0, n_draws); z injected ([n_draws][L]) or Philox keyed on (seed, clip, first_draw + j, l).
-__global__ void __launch_bounds__(256) smooth_inputs_kernel(const float* __restrict__ x, const float* __restrict__ z,
-                                                            float* __restrict__ out, int L, int n_draws, float sigma,
-                                                            float scale, unsigned long long seed, uint32_t clip,
-                                                            long long first_draw) {
-  const long long n = static_cast<long long>(n_draws) * L;
+// Smoothing draws (certified_robust.py:46-54) for a batch of rows that may span several clips.  The work list of a
+// certify call is the clip-major flattening of (clip, draw): row r of this launch is item flat = flat0 + r,
+// clip = flat / per_clip, draw = first_draw + flat % per_clip, and
+//   out[r][l] = scale * (x[clip][l] + sigma * z),   z = zinj[flat][l] (injected, indexed from the start of the call's
+//   [clips][per_clip][L] tensor) or Philox keyed on (seed, clip_key0 + clip, draw, l).
+// Because the key is (clip, draw), how the list is cut into batches or sharded over GPUs never changes a draw.
+// HBM-bound: 4 B written per element (x stays in L2); float4 path when L is a multiple of 4.
+struct SmoothArgs {
+  const float* x;      // [clips][L]
+  const float* zinj;   // or nullptr
+  float* out;          // [n_rows][L]
+  int L, n_rows;
+  long long flat0, per_clip, first_draw;
+  float sigma, scale;
+  unsigned long long seed;
+  uint32_t clip_key0;
+};
+constexpr uint32_t kSmoothStream = 0x534D4F4Fu;  // 'SMOO'
+
+__global__ void __launch_bounds__(256) smooth_inputs_kernel(const SmoothArgs a) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if ((a.L & 3) == 0) {
+    const int L4 = a.L >> 2;
+    const long long n4 = static_cast<long long>(a.n_rows) * L4;
+    for (long long i = tid; i < n4; i += stride) {
+      const long long r = i / L4;
+      const int l = static_cast<int>(i - r * L4) << 2;
+      const long long flat = a.flat0 + r;
+      const long long clip = flat / a.per_clip;
+      const long long draw = a.first_draw + (flat - clip * a.per_clip);
+      float zz[4];
+      if (a.zinj) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.zinj + flat * a.L + l));
+        zz[0] = v.x; zz[1] = v.y; zz[2] = v.z; zz[3] = v.w;
+      } else {
+        philox_normal4(a.seed, kSmoothStream, a.clip_key0 + static_cast<uint32_t>(clip),
+                       (static_cast<uint64_t>(draw) * static_cast<uint64_t>(a.L) + l) >> 2, zz);
+      }
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + clip * a.L + l));
+      float4 o;
+      o.x = a.scale * fmaf(a.sigma, zz[0], xv.x);
+      o.y = a.scale * fmaf(a.sigma, zz[1], xv.y);
+      o.z = a.scale * fmaf(a.sigma, zz[2], xv.z);
+      o.w = a.scale * fmaf(a.sigma, zz[3], xv.w);
+      reinterpret_cast<float4*>(a.out)[i] = o;
+    }
+  } else {
+    const long long n = static_cast<long long>(a.n_rows) * a.L;
+    for (long long i = tid; i < n; i += stride) {
+      const long long r = i / a.L;
+      const int l = static_cast<int>(i - r * a.L);
+      const long long flat = a.flat0 + r;
+      const long long clip = flat / a.per_clip;
+      const long long draw = a.first_draw + (flat - clip * a.per_clip);
+      const float zz = a.zinj ? a.zinj[flat * a.L + l]
+                              : philox_normal(a.seed, kSmoothStream, a.clip_key0 + static_cast<uint32_t>(clip),
+                                              static_cast<uint64_t>(draw) * static_cast<uint64_t>(a.L) + l);
+      a.out[i] = a.scale * fmaf(a.sigma, zz, a.x[clip * a.L + l]);
+    }
+  }
+}
+
+// NES black-box gradient estimation (robustness_eval/_NES.py:15-55), antithetic sampling.  For audio a and sample j
+// of a draw batch of S samples (S even): noise_j = +z_j for j < S/2, -z_{j-S/2} otherwise (_NES.py:19-21), and
+//   eval[a][j][l] = x[a][l] + sigma * noise_j[l]                                            (_NES.py:24)
+// with an optional leading clean row per audio (`lead` = 1 for the first draw batch, _NES.py:22-23).
+// z_j: injected zinj[a][j][l] ([audios][S/2][L]) or Philox keyed on (seed, 'NESG', audio_key0 + a, (draw0 + j) * L + l).
+struct NesArgs {
+  const float* x;     // [audios][L]
+  const float* zinj;  // [audios][S/2][L] or nullptr
+  float* out;         // [audios][lead + S][L]
+  const float* loss;  // [audios][loss_stride]: losses of the S perturbed samples start at loss_off   (grad kernel)
+  float* grad;        // [audios][L], accumulated into                                                (grad kernel)
+  int L, audios, S, lead, loss_stride, loss_off;
+  float sigma, grad_scale;
+  unsigned long long seed;
+  uint32_t audio_key0;
+  long long draw0;
+};
+constexpr uint32_t kNesStream = 0x4E455347u;  // 'NESG'
+
+__device__ __forceinline__ float nes_z(const NesArgs& a, int audio, int j, int l) {
+  return a.zinj ? a.zinj[(static_cast<size_t>(audio) * (a.S / 2) + j) * a.L + l]
+                : philox_normal(a.seed, kNesStream, a.audio_key0 + static_cast<uint32_t>(audio),
+                                static_cast<uint64_t>(a.draw0 + j) * static_cast<uint64_t>(a.L) + l);
+}
+
+__global__ void __launch_bounds__(256) nes_inputs_kernel(const NesArgs a) {
+  const int half = a.S / 2;
+  const long long n = static_cast<long long>(a.audios) * half * a.L;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int l = static_cast<int>(i % L);
-    const long long j = i / L;
-    const float zz = z ? z[i]
-                       : philox_normal(seed, 0x534D4F4Fu /* 'SMOO' */, clip,
-                                       static_cast<uint64_t>(first_draw + j) * static_cast<uint64_t>(L) + l);
-    out[i] = scale * fmaf(sigma, zz, x[l]);
+    const int l = static_cast<int>(i % a.L);
+    const long long aj = i / a.L;
+    const int j = static_cast<int>(aj % half), audio = static_cast<int>(aj / half);
+    const float xv = a.x[static_cast<size_t>(audio) * a.L + l];
+    const float d = a.sigma * nes_z(a, audio, j, l);
+    float* base = a.out + static_cast<size_t>(audio) * (a.lead + a.S) * a.L;
+    base[static_cast<size_t>(a.lead + j) * a.L + l] = d + xv;          // noise * sigma + x (_NES.py:24)
+    base[static_cast<size_t>(a.lead + half + j) * a.L + l] = -d + xv;
+    if (a.lead && j == 0) base[l] = xv;
+  }
+}
+
+// grad[a][l] += grad_scale * sum_j loss[a][j] * noise_j[l] = grad_scale * sum_{j < S/2} (loss_j - loss_{j+S/2}) z_j[l]
+// (_NES.py:44-48,52: mean over the S samples, / sigma / num_batches folded into grad_scale).  The noise is
+// re-generated from its Philox key instead of being kept in HBM (S * L * 4 bytes per audio).
+__global__ void __launch_bounds__(256) nes_grad_kernel(const NesArgs a) {
+  const int half = a.S / 2;
+  const long long n = static_cast<long long>(a.audios) * a.L;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int l = static_cast<int>(i % a.L), audio = static_cast<int>(i / a.L);
+    const float* ls = a.loss + static_cast<size_t>(audio) * a.loss_stride + a.loss_off;
+    float acc = 0.f;
+    for (int j = 0; j < half; ++j) acc = fmaf(ls[j] - ls[half + j], nes_z(a, audio, j, l), acc);
+    a.grad[i] += a.grad_scale * acc;
   }
 }
 
@@ -949,9 +1071,13 @@ __global__ void __launch_bounds__(256) bias_act_kernel(uint4* __restrict__ y, co
   }
 }
 
-// certified_robust.py:58-67: counts[c] += #rows whose argmax is c (lowest index wins ties, like torch.max).
+// certified_robust.py:58-67 for the flattened (clip, draw) work list of smooth_inputs_kernel:
+// counts[sel][clip][c] += #rows whose argmax is c (lowest index wins ties, like torch.max), where row r is item
+// flat0 + r, clip = flat / per_clip and sel = 1 for draws >= n_split (the estimation pass of certify,
+// certified_robust.py:89-93) and 0 otherwise (the selection pass, :84-87).  Integer counts: order-independent.
 __global__ void __launch_bounds__(256) vote_counts_kernel(const float* __restrict__ logits, int rows, int K,
-                                                          unsigned long long* __restrict__ counts) {
+                                                          long long flat0, long long per_clip, long long n_split,
+                                                          int n_clips, unsigned long long* __restrict__ counts) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
     const float* p = logits + static_cast<size_t>(r) * K;
     int best = 0;
@@ -963,7 +1089,10 @@ __global__ void __launch_bounds__(256) vote_counts_kernel(const float* __restric
         best = c;
       }
     }
-    atomicAdd(counts + best, 1ull);
+    const long long flat = flat0 + r;
+    const long long clip = flat / per_clip;
+    const long long sel = (flat - clip * per_clip) >= n_split ? 1 : 0;
+    atomicAdd(counts + (sel * n_clips + clip) * K + best, 1ull);
   }
 }
 

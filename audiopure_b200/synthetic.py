@@ -7,6 +7,7 @@ resnext.py:88-111) drawn from numpy ``PCG64`` streams, so a seed gives the same 
 The zero-initialised output conv (``ZeroConv1d``, WaveNet.py:39-44) is re-randomised, otherwise eps == 0.
 """
 
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -64,8 +65,32 @@ def diffwave_state_dict(seed=1234, wavenet_config=None):
     return sd
 
 
-def resnext_state_dict(seed=4321, nlabels=10, in_channels=1, cardinality=8, depth=29, base_width=64, widen=4):
-    """Random-init ResNeXt-29 8x64 checkpoint (kaiming-normal fan_out convs, unit batch-norm, zero biases)."""
+CALIB_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "resnext_calib.npz")
+
+
+def resnext_state_dict(seed=4321, nlabels=10, in_channels=1, cardinality=8, depth=29, base_width=64, widen=4,
+                       calibrated=True):
+    """Synthetic ResNeXt-29 8x64 checkpoint in the reference layout (resnext.py:88-111).
+
+    ``calibrated=False`` is the constructor's raw init (kaiming-normal fan_out convs, unit batch-norm, zero biases),
+    which maps every log-mel image to the same class.  ``calibrated=True`` (default; seed 4321 only) jitters the
+    batch-norm affine parameters and takes the data-dependent tensors -- batch-norm running statistics measured on
+    synthetic log-mels, and a linear layer centred and scaled on the resulting features -- from
+    ``data/resnext_calib.npz``, so that predictions on ``clips()`` span the classes, with some near-ties."""
+    if calibrated:
+        if not (seed == 4321 and nlabels == 10 and in_channels == 1 and depth == 29):
+            raise ValueError("data/resnext_calib.npz calibrates the seed-4321 ResNeXt-29 with 10 labels only")
+        sd = resnext_state_dict(seed, nlabels, in_channels, cardinality, depth, base_width, widen, calibrated=False)
+        rng2 = np.random.Generator(np.random.PCG64(seed + 1))
+        for k in [k for k in sd if k.endswith("running_mean")]:
+            p = k[:-len(".running_mean")]
+            c = sd[k].numel()
+            sd[p + ".weight"] = torch.from_numpy(rng2.uniform(0.7, 1.3, size=c).astype(np.float32))
+            sd[p + ".bias"] = torch.from_numpy(rng2.normal(0.0, 0.1, size=c).astype(np.float32))
+        with np.load(CALIB_FILE) as cal:
+            for k in cal.files:
+                sd[k] = torch.from_numpy(cal[k].copy())
+        return sd
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = OrderedDict()
 
@@ -107,6 +132,29 @@ def waveforms(batch, length=16000, seed=0):
     """SURVEY.md section 8d synthetic clips: 0.5*(2U-1), shape (B,1,L) fp32 in [-0.5, 0.5)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     return torch.from_numpy((0.5 * (2.0 * rng.random((batch, 1, length)) - 1.0)).astype(np.float32))
+
+
+def clips(batch, length=16000, seed=0, sample_rate=16000):
+    """Structured synthetic clips (B,1,L) fp32 in [-0.9, 0.9]: 1-4 gated, slightly chirped partials at log-uniform
+    frequencies in [80, 7000] Hz over a noise floor of -60..-20 dB, random peak level.  ``waveforms()`` is white
+    noise -- every clip has the same log-mel image up to estimation noise; these differ, so a classifier separates
+    them."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = np.arange(length, dtype=np.float64) / sample_rate
+    out = np.zeros((batch, 1, length), dtype=np.float64)
+    for b in range(batch):
+        y = np.zeros(length, dtype=np.float64)
+        for _ in range(int(rng.integers(1, 5))):
+            f0 = 80.0 * (7000.0 / 80.0) ** rng.random()
+            chirp = rng.uniform(-0.5, 0.5) * f0
+            amp = rng.uniform(0.2, 1.0)
+            on = rng.uniform(0.0, 0.6)
+            dur = rng.uniform(0.15, 0.8)
+            env = np.clip((t - on) / 0.02, 0.0, 1.0) * np.clip((on + dur - t) / 0.02, 0.0, 1.0)
+            y += amp * env * np.sin(2.0 * np.pi * (f0 * t + 0.5 * chirp * t * t) + rng.uniform(0.0, 2.0 * np.pi))
+        y += 10.0 ** rng.uniform(-3.0, -1.0) * rng.standard_normal(length)
+        out[b, 0] = y * (rng.uniform(0.2, 0.9) / np.abs(y).max())
+    return torch.from_numpy(out.astype(np.float32))
 
 
 def noise(shape, seed=7):

@@ -4,15 +4,23 @@
 
 Workload (config.workload): BASELINE configs[1] -- DDPM t*=2 purification of a batch of 64 synthetic
 1-s 16 kHz clips through the 36-layer DiffWave, then log-mel and the ResNeXt-29 8x64 classifier, bf16
-tensor cores.  One process per GPU; with N > 1 every rank purifies its own 64 clips (weak scaling, no
-collective on the data path) and `value` = clips of all ranks / max-over-ranks device time.
+tensor cores.  One process per GPU (`--gpus N` without a torchrun environment re-launches itself under
+torch.distributed.run); with N > 1 every rank purifies its own 64 clips (weak scaling, no collective on the data
+path) and `value` = clips of all ranks / max-over-ranks device time.
 
-A "step" = one pass over one batch.  `value` has the batch resident in HBM; `e2e` goes through the public
-API (AcousticSystem.forward) from pinned HOST memory and reads the predictions back, copies inside the
-timed region.  `roofline` describes the dominant kernel (the fused residual-layer kernel, 36 launches per
-network evaluation) timed with CUDA events on its own stream during the timed region (ap_profile_*).
-`cpu_baseline` / `--impl reference`: the oracle port of the reference's fp32 CPU path on this box's host
-cores, on a bounded sample (the reference is Python and cannot travel to the GPU box).
+A "step" = one pass over one batch.  Three passes of K steps each: (1) `value`, batch resident in HBM, launches
+back to back with programmatic dependent launch live; (2) the same steps with every launch bracketed by CUDA
+events on its own stream (ap_profile_*), which feeds `roofline` (the fused residual-layer kernel, 36 launches per
+network evaluation) and `kernels`; (3) `e2e`, through the public API (AcousticSystem.forward) from pinned HOST
+memory with the predictions read back, copies inside the timed region.
+
+Second leg, `certify` (BASELINE configs[3], the one path with a collective): randomized-smoothing certification of
+4 clips x (n_0 = 100 + n = 10 000) draws at sigma = 0.25, the SAME total work at every N (strong scaling), draws
+sharded over the ranks, vote counts summed by ONE ncclAllReduce(int64) inside the timed region (`collective`).
+
+`cpu_baseline` / `--impl reference`: the reference's own fp32 CPU path on this box's host cores at BASELINE
+configs[0]'s batch of 4 -- the unmodified reference files staged under oracle/_ref when present (kind
+"reference"), else the oracle port (kind "port").
 """
 
 import argparse
@@ -43,7 +51,11 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--t-star", type=int, default=T_STAR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-clips", type=int, default=1)
+    ap.add_argument("--cpu-sample-clips", type=int, default=4, help="clips per CPU step (BASELINE configs[0]: batch 4)")
+    ap.add_argument("--no-certify", action="store_true", help="skip the certification leg")
+    ap.add_argument("--certify-clips", type=int, default=4)
+    ap.add_argument("--certify-n", type=int, default=10000)
+    ap.add_argument("--certify-n0", type=int, default=100)
     ap.add_argument("--purifier", default="ddpm", choices=["ddpm", "sde"],
                     help="ddpm: DiffWave.forward (BASELINE configs[1], the headline); sde: RevDiffWave (configs[2])")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
@@ -115,25 +127,47 @@ def measured_peak():
 
 
 # -------------------------------------------------------------------------------- CPU reference arm --
-def cpu_reference_step(n_clips, t_star, state):
-    """One bounded sample of the reference's CPU path (oracle port, fp32, all host threads):
-    DDPM t* purify -> log-mel -> ResNeXt-29 on n_clips clips."""
+def cpu_reference_setup(n_clips, t_star):
+    """The reference's CPU path for BASELINE configs[0]: the UNMODIFIED reference files (oracle/_ref, staged by
+    __graft_entry__.build()) when present, else the oracle port.  Returns (step_fn, kind, description)."""
     import torch
-    from oracle import mel as o_mel, purify as o_purify, resnext as o_resnext, schedule as o_schedule, \
-        wavenet as o_wavenet, weights as W
+    from oracle import _refharness, resnext as o_resnext, stage_ref, weights as W
 
-    if not state:
-        torch.set_num_threads(os.cpu_count())
-        state["sd"] = W.make_state_dict(1234)
-        state["csd"] = o_resnext.make_state_dict(4321)
-        state["hp"] = o_schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
-        state["x"] = W.make_waveforms(n_clips, CLIP_LEN, seed=0)
-        state["z"] = W.make_noise((t_star, n_clips, 1, CLIP_LEN), seed=7)
-    sd = state["sd"]
-    with torch.no_grad():
-        y = o_purify.ddpm_purify(state["hp"], lambda xx, t: o_wavenet.eps_theta(sd, xx, t), state["x"], t_star, state["z"])
-        logits = o_resnext.forward(state["csd"], o_mel.log_mel(y))
-    return logits.argmax(1)
+    torch.set_num_threads(os.cpu_count())
+    x = W.make_clips(n_clips, CLIP_LEN, seed=0)
+    sd, csd = W.make_state_dict(1234), o_resnext.make_state_dict(4321)
+    what = "%d clips per step (BASELINE configs[0] batch): DDPM t*=%d purify + log-mel + ResNeXt-29, fp32, " % (n_clips, t_star)
+    if stage_ref.available():
+        ref = _refharness.load(root=_refharness.STAGED_ROOT, cpu=True)
+        model = ref.wavenet.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
+        model.load_state_dict(sd)
+        hp = ref.util.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+        dw = ref.ddpm.DiffWave(model=model.eval(), diffusion_hyperparams=hp, reverse_timestep=t_star)
+        clf = ref.resnext.CifarResNeXt(nlabels=10, in_channels=1)
+        clf.load_state_dict(csd)
+        ta = ref.torchaudio.transforms
+        mel = ta.MelSpectrogram(n_fft=2048, hop_length=512, n_mels=32, norm="slaney", pad_mode="constant", mel_scale="slaney")
+        a2db = ta.AmplitudeToDB(stype="power")
+        system = ref.acoustic_system.AcousticSystem(classifier=clf.eval(), transform=lambda w: a2db(mel(w)), defender=dw,
+                                                    defense_type="wave")
+
+        def step():
+            with torch.no_grad():
+                return system(x).max(1)[1]
+
+        return step, "reference", what + "the reference's own unmodified modules (oracle/_ref) through AcousticSystem.forward"
+
+    from oracle import mel as o_mel, purify as o_purify, schedule as o_schedule, wavenet as o_wavenet
+
+    hp = o_schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    z = W.make_noise((t_star, n_clips, 1, CLIP_LEN), seed=7)
+
+    def step():
+        with torch.no_grad():
+            y = o_purify.ddpm_purify(hp, lambda xx, t: o_wavenet.eps_theta(sd, xx, t), x, t_star, z)
+            return o_resnext.forward(csd, o_mel.log_mel(y)).argmax(1)
+
+    return step, "port", what + "oracle port of the reference (oracle/_ref not staged)"
 
 
 def run_reference(args):
@@ -142,23 +176,22 @@ def run_reference(args):
         return
     import torch
 
-    state = {}
     n = args.cpu_sample_clips
+    step, kind, sample = cpu_reference_setup(n, args.t_star)
     for _ in range(args.warmup):
-        cpu_reference_step(n, args.t_star, state)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(n, args.t_star, state)
+        step()
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     cores = torch.get_num_threads()
-    sample = "%d clip(s) per step: DDPM t*=%d purify + log-mel + ResNeXt-29, fp32, oracle port of the reference" % (n, args.t_star)
     line = {
         "impl": "reference", "metric": "purified 1-s clips/sec", "value": value, "unit": "clips/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,8 +200,10 @@ def run_reference(args):
 
 def workload_config(args):
     return {
-        "workload": "BASELINE configs[%d]: %s t*=%d purification + log-mel + ResNeXt-29 8x64, batch %d synthetic "
-                    "1-s 16 kHz clips per GPU, DiffWave-unconditional (36 layers, 256 ch, T=200), random-init weights"
+        "workload": "BASELINE configs[%d]: %s t*=%d purification + log-mel + ResNeXt-29 8x64 on synthetic 1-s 16 kHz "
+                    "clips, DiffWave-unconditional (36 layers, 256 ch, T=200), random-init weights; the GPU arm runs "
+                    "batch %d per GPU, the CPU reference arm a bounded sample of the same workload at configs[0]'s "
+                    "batch (see cpu_baseline.sample)"
                     % (1 if args.purifier == "ddpm" else 2, "DDPM" if args.purifier == "ddpm" else "reverse VP-SDE",
                        args.t_star, args.batch),
         "batch_per_gpu": args.batch, "t_star": args.t_star, "clip_samples": CLIP_LEN,
@@ -178,6 +213,89 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm --
+TAIL_GFLOP_PER_CLIP = (2 * 256 * (36 * 256) * 16000 + 2 * 256 * 256 * 16000 + 2 * 256 * 16000) / 1e9  # skip K=9216 + head
+
+
+def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
+    """BASELINE configs[3]: randomized-smoothing certification, draws sharded over the ranks, the int64 vote counts
+    summed by one ncclAllReduce through the C ABI (ap_allreduce_counts).  Strong scaling: the total work is the
+    same at every N.  The collective is inside the timed region; its own time is measured with events around it."""
+    import torch
+    import torch.distributed as dist
+
+    from audiopure_b200 import _lib
+    from audiopure_b200.certified_robust import NcclCountsAllReduce
+
+    class TimedAllReduce(NcclCountsAllReduce):
+        calls, bytes, spans = 0, 0, []
+
+        def __call__(self, counts):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = super().__call__(counts)
+            e1.record()
+            self.calls += 1
+            self.bytes += counts.numel() * counts.element_size()
+            self.spans.append((e0, e1))
+            return out
+
+    allreduce = TimedAllReduce(rank, world)  # a 1-rank communicator at N = 1: the same call path at every N
+    n0, n, clips, sigma, bs = args.certify_n0, args.certify_n, args.certify_clips, 0.25, 64
+    dw = ap.DiffWave(model, hp, reverse_timestep=34, seed=0)
+    RC = ap.RobustCertificate(clf, ap.LogMelSpectrogram().to(dev), dw, seed=5, rank=rank, world_size=world,
+                              allreduce=allreduce)
+    x = S.clips(clips, CLIP_LEN, seed=3).to(dev)
+    y = torch.zeros(clips, dtype=torch.long, device=dev)
+    total = clips * (n0 + n)
+
+    def run():
+        return RC.certify(x, y, sigma=sigma, n_0=n0, n=n, batch_size=bs, clip_offset=0)
+
+    run()  # warm-up with exactly the timed call's batch shapes (cuDNN autotunes per shape, ragged last batch included)
+    TimedAllReduce.calls, TimedAllReduce.bytes, TimedAllReduce.spans = 0, 0, []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    y_pred, radius = run()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    coll_ms = sum(a.elapsed_time(b) for a, b in TimedAllReduce.spans)
+    counts_0, counts = RC.last_counts
+    certify = {
+        "workload": "BASELINE configs[3]: %d clips x (n_0 = %d + n = %d) smoothing draws, sigma = %.2f (t* = 34): "
+                    "one-shot denoise + log-mel + ResNeXt-29 per draw, batches of %d spanning clips, strong scaling"
+                    % (clips, n0, n, sigma, bs),
+        "draws_per_s": total / (ms * 1e-3), "seconds_per_clip": ms * 1e-3 / clips, "ms": ms, "n": n, "n0": n0,
+        "clips": clips, "n_gpus": world, "scaling": "strong",
+        "y_pred": y_pred.tolist(), "radius": [round(float(r), 4) for r in radius.tolist()],
+        "counts_checksum": int((counts * torch.arange(1, 11)).sum() + 31 * (counts_0 * torch.arange(1, 11)).sum()),
+    }
+    collective = {"name": "ncclAllReduce int64 sum (ap_allreduce_counts, NCCL via dlopen)", "calls": TimedAllReduce.calls,
+                  "bytes": TimedAllReduce.bytes, "ms": coll_ms, "nranks": world,
+                  "where": "inside the certify timed region, once per certify call"}
+    return certify, collective
+
+
+def relaunch_under_torchrun(args):
+    """`python bench.py --gpus N` without a torchrun environment: start N ranks on this node and relay their output."""
+    import socket
+
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    sys.exit(subprocess.call(cmd))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -188,6 +306,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if "WORLD_SIZE" not in os.environ and args.gpus > 1:
+        relaunch_under_torchrun(args)
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d; launch with torch.distributed.run --nproc-per-node %d"
+                         % (args.gpus, world, args.gpus))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True  # as the reference's eval scripts do (adaptive_attack_eval.py:69)
@@ -212,7 +335,7 @@ def run_ours(args):
     eng = model.engine()
 
     B = args.batch
-    x_host = S.waveforms(B, CLIP_LEN, seed=rank).pin_memory()
+    x_host = S.clips(B, CLIP_LEN, seed=rank).pin_memory()
     x_dev = x_host.to(dev)
 
     def step_resident():
@@ -242,14 +365,19 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # pass 1: the headline.  No events between launches, so programmatic dependent launch overlaps every kernel's
+    # set-up with its predecessor's tail, as in production use.
+    ms = timed(step_resident, args.steps)
+    # pass 2: the same steps with every launch bracketed by events on its stream -> per-kernel device time
     eng.profile(True)
     eng.profile_read()
-    ms = timed(step_resident, args.steps)
+    ms_prof = timed(step_resident, args.steps)
     prof = eng.profile_read()
     eng.profile(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -261,17 +389,25 @@ def run_ours(args):
     total_clips = B * world * args.steps
     value = total_clips / (ms * 1e-3)
     layer_ms, layer_n = prof["layer"]
-    evals_per_step = args.t_star * ((B + model.max_chunk - 1) // model.max_chunk)
-    launches_per_step = (1 + evals_per_step * (model.num_res_layers + 2)) + ((B + model.max_chunk - 1) // model.max_chunk - 1) + 1
+    chunks = (B + model.max_chunk - 1) // model.max_chunk
+    evals_per_step = args.t_star * chunks
+    launches_per_step = chunks * (1 + args.t_star * (model.num_res_layers + 2)) + 1  # diffuse + evals; log-mel (ours)
     peak, peak_src = measured_peak()
     if args.precision == "tf32":  # no measured tf32 figure: the tensor core's tf32 rate is half its bf16 rate
         peak, peak_src = peak / 2, peak_src + " / 2 (tf32 = half the bf16 rate)"
     clips_per_launch = min(B, model.max_chunk)
-    achieved = clips_per_launch * LAYER_GFLOP_PER_CLIP / (layer_ms / max(layer_n, 1)) if layer_n else 0.0  # GFLOP/ms = TFLOP/s
+    avg_layer_ms = layer_ms / max(layer_n, 1)
+    achieved = clips_per_launch * LAYER_GFLOP_PER_CLIP / avg_layer_ms if layer_n else 0.0  # GFLOP/ms = TFLOP/s
+    tail_ms = prof["tail"][0] / max(prof["tail"][1], 1)
+    pro_ms = prof["prologue"][0] / max(prof["prologue"][1], 1)
+    hbm = None
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        hbm = json.load(open(pk)).get("hbm_gbs")
 
     line = {
         "metric": "purified 1-s clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
         "clocks": clocks,
         "e2e": {"value": total_clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
@@ -284,12 +420,30 @@ def run_ours(args):
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak else None, "peak_source": peak_src,
             "flop_per_launch": clips_per_launch * LAYER_GFLOP_PER_CLIP * 1e9,
-            "avg_launch_ms": layer_ms / max(layer_n, 1), "launches_timed": layer_n,
-            "share_of_step": layer_ms / ms if ms else None,
-            "tail_kernel_ms_per_launch": prof["tail"][0] / max(prof["tail"][1], 1),
+            "avg_launch_ms": avg_layer_ms, "launches_timed": layer_n,
+            "share_of_step": layer_ms / ms_prof if ms_prof else None,
+            "timed_in": "pass 2 (events around every launch; %.3f ms/step vs %.3f ms/step in the untouched pass 1)"
+                        % (ms_prof / args.steps, ms / args.steps),
+            "tail_kernel_ms_per_launch": tail_ms,
             "traffic": None,
         },
+        "kernels": {
+            "tail_kernel": {"bound": "tensor", "ms_per_launch": tail_ms,
+                            "achieved_tflops": clips_per_launch * TAIL_GFLOP_PER_CLIP / tail_ms if tail_ms else None,
+                            "frac": (clips_per_launch * TAIL_GFLOP_PER_CLIP / tail_ms / peak) if tail_ms and peak else None},
+            "prologue_kernel": {"bound": "hbm", "ms_per_launch": pro_ms,
+                                "achieved_gbs": clips_per_launch * CLIP_LEN * (4 + 512 * (2 if args.precision == "tf32" else 1)) / pro_ms / 1e6 if pro_ms else None,
+                                "peak_gbs": hbm},
+            "residual_stack_tflops": (clips_per_launch * (36 * LAYER_GFLOP_PER_CLIP + TAIL_GFLOP_PER_CLIP)
+                                      / (36 * avg_layer_ms + tail_ms)) if layer_n and tail_ms else None,
+        },
     }
+    if line["kernels"]["prologue_kernel"]["achieved_gbs"] and hbm:
+        line["kernels"]["prologue_kernel"]["frac"] = line["kernels"]["prologue_kernel"]["achieved_gbs"] / hbm
+    if not args.no_certify:
+        cert, coll = certify_leg(args, ap, S, model, hp, clf, dev, rank, world)
+        line["certify"] = cert
+        line["collective"] = coll
     if world == 1 and not args.no_same_box_peak:
         # Supplementary evidence, not the roofline denominator: what cuBLAS bf16 (8192^3, back to back for ~3 s)
         # sustains on THIS box right after the timed region, with its power draw -- the step is power-capped, and
@@ -322,18 +476,14 @@ def run_ours(args):
             "how": "torch.matmul bf16 8192^3 back to back for 3 s on this GPU after the timed region"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            state = {}
             n = args.cpu_sample_clips
-            cpu_reference_step(n, args.t_star, state)  # warm-up
+            step, kind, sample = cpu_reference_setup(n, args.t_star)
+            step()  # warm-up
             t0 = time.perf_counter()
-            reps = 2
-            for _ in range(reps):
-                cpu_reference_step(n, args.t_star, state)
-            dt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = {
-                "value": n / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                "sample": "%d clip(s), DDPM t*=%d purify + log-mel + ResNeXt-29, fp32 oracle port, 1 warm-up + %d timed"
-                          % (n, args.t_star, reps)}
+            step()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
+                                    "sample": sample + "; 1 warm-up + 1 timed step"}
         traffic_file = os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")
         if os.path.exists(traffic_file) and args.precision == "bf16":  # the ncu capture is of the bf16 kernel
             line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AP_ABI_VERSION 5
+#define AP_ABI_VERSION 6
 
 typedef struct ap_net ap_net;   /* the packed DiffWave epsilon-network + its diffusion schedule */
 typedef struct ap_comm ap_comm; /* an NCCL communicator for the vote-count all-reduce           */
@@ -143,6 +143,33 @@ int ap_smooth_inputs(const float* x, int L, int n_draws, float sigma, float scal
 /* certified_robust.py:58-67: counts[c] += #{rows : argmax_k logits[row][k] == c}; counts is int64[K] and
  * is accumulated into (zero it first).                                                                   */
 int ap_vote_counts(const float* logits, int rows, int K, int64_t* counts, void* stream);
+
+/* The same two steps for a certify call over SEVERAL clips (certified_robust.py:81-96), so that every launch is a
+ * full batch whatever n_0, n and the number of ranks are.  The call's work list is the clip-major flattening of
+ * (clip, draw), draw in [0, per_clip): row r of a launch is item flat = flat0 + r, clip = flat / per_clip,
+ * draw = first_draw + flat % per_clip.
+ *   ap_smooth_inputs_batch: out[r][l] = scale * (x[clip][l] + sigma * z); z injected ([clips][per_clip][L], indexed
+ *     by flat) or NULL -> Philox keyed on (seed, clip_key0 + clip, draw, l) -- the draws do not depend on how the
+ *     list is batched or sharded.
+ *   ap_vote_counts_batch: counts[sel][clip][argmax] += 1 with sel = (flat % per_clip >= n_split); counts is
+ *     int64[2][n_clips][K] (selection pass n_0 | estimation pass n of certify), accumulated into.            */
+int ap_smooth_inputs_batch(const float* x, int L, int n_rows, int64_t flat0, int64_t per_clip, int64_t first_draw,
+                           float sigma, float scale, const float* z, uint64_t seed, uint32_t clip_key0, float* out,
+                           void* stream);
+int ap_vote_counts_batch(const float* logits, int rows, int K, int64_t flat0, int64_t per_clip, int64_t n_split,
+                         int n_clips, int64_t* counts, void* stream);
+
+/* NES black-box gradient estimation with antithetic sampling (robustness_eval/_NES.py:15-55), one draw batch of S
+ * samples (S even) per audio:
+ *   ap_nes_inputs: out[a][lead + j][l] = x[a][l] + sigma * noise_j[l], noise_j = +z_j (j < S/2), -z_{j-S/2} otherwise
+ *     (_NES.py:19-24); lead = 1 prepends the clean audio (first draw batch, _NES.py:22-23).  out: [audios][lead+S][L].
+ *     z: injected [audios][S/2][L] or NULL -> Philox keyed on (seed, audio_key0 + a, draw0 + j, l).
+ *   ap_nes_grad: grad[a][l] += grad_scale * sum_j loss[a][loss_off + j] * noise_j[l]   (_NES.py:44-48,52), the noise
+ *     re-generated from the same keys (or read from the same z) instead of being kept in HBM.                   */
+int ap_nes_inputs(const float* x, int audios, int L, int S, int lead, float sigma, const float* z, uint64_t seed,
+                  uint32_t audio_key0, int64_t draw0, float* out, void* stream);
+int ap_nes_grad(const float* loss, int loss_stride, int loss_off, int audios, int L, int S, float grad_scale,
+                const float* z, uint64_t seed, uint32_t audio_key0, int64_t draw0, float* grad, void* stream);
 
 /* Consumer-side epilogue of the ResNeXt bottleneck after batch-norm folding (resnext.py:56-64):
  *   y[r][c] = relu?(y[r][c] + bias[c] (+ residual[r][c]))      in place, y/residual channels-last bf16 [rows][C],

@@ -1,8 +1,9 @@
-"""Oracle tooling (test infrastructure): import the UNMODIFIED reference on CPU.
+"""Oracle tooling (test infrastructure): import the UNMODIFIED reference.
 
-Only usable where ``/root/reference`` exists (the build container); nothing
-under ``tests -m gpu``, ``smoke()`` or ``bench.py`` calls this.  Used by
-``oracle/make_golden.py`` to generate the committed fixtures.
+Two roots: ``/root/reference`` (the build container; used by ``oracle/make_golden.py`` to generate the committed
+fixtures) and ``oracle/_ref`` (the hot-path files staged by ``oracle/stage_ref.py``, which travel to the GPU box;
+used by ``bench.py --impl reference`` and ``tools/gpu_eager_reference.py``).  Nothing under ``tests -m gpu`` or
+``smoke()`` calls this.
 
 Recipe: put the checkout on ``sys.path``, stub the
 absent third-party imports, and make ``.cuda()`` the identity so the
@@ -17,21 +18,25 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("AUDIOPURE_REFERENCE", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
-def available():
-    return os.path.isdir(os.path.join(REF_ROOT, "diffusion_models"))
+def available(root=None):
+    return os.path.isdir(os.path.join(root or REF_ROOT, "diffusion_models"))
 
 
-def load():
-    """Returns a namespace with the reference modules needed on the hot path."""
-    if not available():
-        raise RuntimeError("reference checkout not present at %s" % REF_ROOT)
+def load(root=None, cpu=True):
+    """Returns a namespace with the reference modules needed on the hot path.  ``cpu=True`` makes ``.cuda()`` the
+    identity (the reference hard-codes device moves); ``cpu=False`` leaves it alone: the same files then run as the
+    GPU fp32 reference."""
+    root = root or REF_ROOT
+    if not available(root):
+        raise RuntimeError("reference files not present at %s" % root)
     import torch
     import torchaudio
 
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     for name in ("librosa", "torchsde"):
         if name not in sys.modules:
             try:
@@ -58,8 +63,9 @@ def load():
     for fn in ("download_url", "extract_archive"):
         if not hasattr(tdu, fn):
             setattr(tdu, fn, lambda *a, **k: None)
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
+    if cpu:
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
 
     ns = types.SimpleNamespace()
     ns.ddpm = importlib.import_module("diffusion_models.diffwave_ddpm")
@@ -69,8 +75,9 @@ def load():
     ns.acoustic_system = importlib.import_module("acoustic_system")
     ns.certified = importlib.import_module("robustness_eval.certified_robust")
     spec = importlib.util.spec_from_file_location(
-        "_ref_resnext", os.path.join(REF_ROOT, "audio_models/ConvNets_SpeechCommands/models/resnext.py"))
+        "_ref_resnext", os.path.join(root, "audio_models/ConvNets_SpeechCommands/models/resnext.py"))
     ns.resnext = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ns.resnext)
     ns.torchaudio = torchaudio
+    ns.root = root
     return ns

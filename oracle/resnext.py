@@ -7,6 +7,7 @@ reference-layout state dict.  The classifier is a *consumer* of the hot path
 restatement exists so logits / votes can be checked on the CPU.
 """
 
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -38,29 +39,59 @@ def _bn(sd, prefix, x):
                         sd[prefix + ".weight"], sd[prefix + ".bias"], training=False, eps=1e-5)
 
 
-def forward(sd, x):
-    """resnext.py:134-142 over state dict ``sd``; x: (B,1,32,32) -> (B,nlabels)."""
+def features(sd, x, bn=_bn):
+    """resnext.py:134-140 (everything before the linear layer): (B,1,32,32) -> (B,1024).  ``bn`` is replaceable so
+    that oracle/calibrate_resnext.py can collect batch statistics with the same dataflow."""
     stages, plan = _stage_plan()
-    x = F.relu(_bn(sd, "bn_1", F.conv2d(x, sd["conv_1_3x3.weight"], padding=1)))
+    x = F.relu(bn(sd, "bn_1", F.conv2d(x, sd["conv_1_3x3.weight"], padding=1)))
     for name, cin, cout, stride, D in plan:
-        b = F.relu(_bn(sd, name + ".bn_reduce", F.conv2d(x, sd[name + ".conv_reduce.weight"])))
-        b = F.relu(_bn(sd, name + ".bn", F.conv2d(b, sd[name + ".conv_conv.weight"], stride=stride, padding=1,
-                                                   groups=CARDINALITY)))
-        b = _bn(sd, name + ".bn_expand", F.conv2d(b, sd[name + ".conv_expand.weight"]))
+        b = F.relu(bn(sd, name + ".bn_reduce", F.conv2d(x, sd[name + ".conv_reduce.weight"])))
+        b = F.relu(bn(sd, name + ".bn", F.conv2d(b, sd[name + ".conv_conv.weight"], stride=stride, padding=1,
+                                                  groups=CARDINALITY)))
+        b = bn(sd, name + ".bn_expand", F.conv2d(b, sd[name + ".conv_expand.weight"]))
         if cin != cout:
-            r = _bn(sd, name + ".shortcut.shortcut_bn",
-                    F.conv2d(x, sd[name + ".shortcut.shortcut_conv.weight"], stride=stride))
+            r = bn(sd, name + ".shortcut.shortcut_bn",
+                   F.conv2d(x, sd[name + ".shortcut.shortcut_conv.weight"], stride=stride))
         else:
             r = x
         x = F.relu(r + b)
     x = F.avg_pool2d(x, 8, 1)
-    x = x.view(-1, stages[3])
-    return F.linear(x, sd["classifier.weight"], sd["classifier.bias"])
+    return x.view(-1, stages[3])
 
 
-def make_state_dict(seed=4321, nlabels=10, in_channels=1):
-    """Deterministic random init in the reference layout (resnext.py:88-111: kaiming-normal
-    fan_out convs, unit batch-norm scale, zero biases), from a numpy PCG64 stream."""
+def forward(sd, x):
+    """resnext.py:134-142 over state dict ``sd``; x: (B,1,32,32) -> (B,nlabels)."""
+    return F.linear(features(sd, x), sd["classifier.weight"], sd["classifier.bias"])
+
+
+CALIB_FILE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "audiopure_b200", "data",
+                          "resnext_calib.npz")
+
+
+def make_state_dict(seed=4321, nlabels=10, in_channels=1, calibrated=True):
+    """Deterministic synthetic checkpoint in the reference layout, from a numpy PCG64 stream.
+
+    ``calibrated=False``: the constructor's own init (resnext.py:88-111: kaiming-normal fan_out convs, unit
+    batch-norm, zero biases) -- it predicts one class for every log-mel input.  ``calibrated=True`` (default, seed
+    4321 only): batch-norm affine parameters are jittered (scale U(0.7,1.3), shift N(0,0.1)) and the
+    data-dependent tensors -- batch-norm running statistics and the centred, rescaled linear layer -- are read
+    from ``audiopure_b200/data/resnext_calib.npz`` (written once by oracle/calibrate_resnext.py), so predictions
+    on synthetic clips span the classes and some are near-ties."""
+    if calibrated:
+        assert seed == 4321 and nlabels == 10 and in_channels == 1, "the calibration file is for seed 4321"
+        sd = make_state_dict(seed, nlabels, in_channels, calibrated=False)
+        rng2 = np.random.Generator(np.random.PCG64(seed + 1))
+        for k in [k for k in sd if k.endswith("running_mean")]:
+            p = k[:-len(".running_mean")]
+            c = sd[k].numel()
+            sd[p + ".weight"] = torch.from_numpy(rng2.uniform(0.7, 1.3, size=c).astype(np.float32))
+            sd[p + ".bias"] = torch.from_numpy(rng2.normal(0.0, 0.1, size=c).astype(np.float32))
+        if os.path.exists(CALIB_FILE):  # absent only while oracle/calibrate_resnext.py is creating it
+            with np.load(CALIB_FILE) as cal:
+                for k in cal.files:
+                    assert tuple(cal[k].shape) == tuple(sd[k].shape), k
+                    sd[k] = torch.from_numpy(cal[k].copy())
+        return sd
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = OrderedDict()
 

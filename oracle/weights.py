@@ -92,6 +92,30 @@ def make_waveforms(batch, length=16000, seed=0):
     return torch.from_numpy((0.5 * (2.0 * rng.random((batch, 1, length)) - 1.0)).astype(np.float32))
 
 
+def make_clips(batch, length=16000, seed=0, sample_rate=16000):
+    """Structured synthetic clips (B,1,L) fp32 in [-0.9, 0.9]: 1-4 gated, slightly chirped partials at log-uniform
+    frequencies in [80, 7000] Hz over a noise floor of -60..-20 dB, random peak level.  Unlike ``make_waveforms``
+    (white noise: every clip has the same log-mel image up to estimation noise) these give the classifier
+    inputs that differ, so top-1 / vote-count comparisons can fail.  Same generator as
+    ``audiopure_b200.synthetic.clips`` (kept in step by tests/test_packing.py)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = np.arange(length, dtype=np.float64) / sample_rate
+    out = np.zeros((batch, 1, length), dtype=np.float64)
+    for b in range(batch):
+        y = np.zeros(length, dtype=np.float64)
+        for _ in range(int(rng.integers(1, 5))):
+            f0 = 80.0 * (7000.0 / 80.0) ** rng.random()
+            chirp = rng.uniform(-0.5, 0.5) * f0
+            amp = rng.uniform(0.2, 1.0)
+            on = rng.uniform(0.0, 0.6)
+            dur = rng.uniform(0.15, 0.8)
+            env = np.clip((t - on) / 0.02, 0.0, 1.0) * np.clip((on + dur - t) / 0.02, 0.0, 1.0)
+            y += amp * env * np.sin(2.0 * np.pi * (f0 * t + 0.5 * chirp * t * t) + rng.uniform(0.0, 2.0 * np.pi))
+        y += 10.0 ** rng.uniform(-3.0, -1.0) * rng.standard_normal(length)
+        out[b, 0] = y * (rng.uniform(0.2, 0.9) / np.abs(y).max())
+    return torch.from_numpy(out.astype(np.float32))
+
+
 def make_noise(shape, seed=7):
     """Pre-drawn standard normal noise to inject into both implementations."""
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -13,19 +13,15 @@ import audiopure_b200 as ap
 from audiopure_b200 import _lib
 from audiopure_b200.wavenet import round_to_tf32
 from oracle import purify as o_purify, schedule as o_schedule, wavenet as o_wavenet, weights as W
+from tests import gates
 from tests.emulate import emulate_eps_tf32
+from tests.gates import check_eps, check_wave, rel_l2, zero_eps
 
 pytestmark = pytest.mark.gpu
 
-EPS_GATE_TF32 = 2e-3
-WAVE_GATE_TF32 = 1e-3
+EPS_GATE_TF32 = gates.EPS_GATE["tf32"]
+WAVE_GATE_TF32 = gates.WAVE_GATE["tf32"]
 SMALL = dict(W.DEFAULT_WAVENET_CONFIG, num_res_layers=6, dilation_cycle=3)
-
-
-def rel_l2(a, b):
-    a = torch.as_tensor(a).detach().double().cpu()
-    b = torch.as_tensor(b).detach().double().cpu()
-    return float((a - b).norm() / b.norm())
 
 
 def make_model(cfg, seed, **kw):
@@ -130,7 +126,8 @@ def test_eps_full_vs_golden(full_model, golden, t):
     g = golden("wavenet_full.npz")
     x = W.make_waveforms(1, 16000, seed=0)
     got = full_model.engine().eps(x.cuda(), t)
-    assert rel_l2(got, g["eps_t%d" % t]) < EPS_GATE_TF32
+    tot, acv = check_eps(got, g["eps_t%d" % t], mode="tf32")
+    print("tf32 eps t=%d: rel-L2 %.3e, mean-removed %.3e" % (t, tot, acv))
 
 
 def test_eps_is_batch_invariant_and_chunked(full_model):
@@ -166,7 +163,9 @@ def test_ddpm_purify_vs_reference(full_model, hp, golden, t_star):
     x = W.make_waveforms(2, 16000, seed=int(g["x_seed"]))
     z = W.make_noise((t_star, 2, 1, 16000), seed=int(g["z_seed"]))
     dw = ap.DiffWave(full_model, hp, reverse_timestep=t_star)
-    assert rel_l2(dw(x.cuda(), z=z), g["purified"]) < WAVE_GATE_TF32
+    o_hp = o_schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    tot, net = check_wave(dw(x.cuda(), z=z), g["purified"], o_purify.ddpm_purify(o_hp, zero_eps, x, t_star, z), mode="tf32")
+    print("tf32 ddpm t*=%d: waveform rel-L2 %.3e, error / network contribution %.3e" % (t_star, tot, net))
 
 
 def test_one_shot_vs_reference(full_model, hp, golden):
@@ -174,7 +173,18 @@ def test_one_shot_vs_reference(full_model, hp, golden):
     g = golden("oneshot_t34.npz")
     x = W.make_waveforms(1, 16000, seed=0)
     dw = ap.DiffWave(full_model, hp, reverse_timestep=int(g["reverse_timestep"]))
-    assert rel_l2(dw.one_shot_denoise(x.cuda()), g["x0_hat"]) < WAVE_GATE_TF32
+    o_hp = o_schedule.calc_diffusion_hyperparams(**W.DEFAULT_DIFFUSION_CONFIG)
+    check_wave(dw.one_shot_denoise(x.cuda()), g["x0_hat"], o_purify.one_shot_denoise(o_hp, zero_eps, x, 34), mode="tf32")
+
+
+def test_sde_t5_vs_reference_drift(full_model, hp, golden):
+    g = golden("sde_t5.npz")
+    t = int(g["t"])
+    x = W.make_clips(2, 16000, seed=int(g["x_seed"]))
+    z = W.make_noise((t + 1, 2, 1, 16000), seed=int(g["z_seed"]))
+    got = full_model.engine().sde_purify(x.cuda(), t, z=z)
+    y0 = o_purify.sde_purify(o_schedule.sde_tables(), zero_eps, x, t, z[0], z[1:].reshape(t, 2, 16000))
+    check_wave(got, g["purified"], y0, mode="tf32", what="tf32 sde t=5")
 
 
 def test_sde_purify_vs_oracle(small_model):
@@ -218,12 +228,7 @@ def test_top1_agreement_bf16_vs_tf32_on_512_clips(full_model, hp):
     m16 = ap.WaveNet_Speech_Commands(**W.DEFAULT_WAVENET_CONFIG)
     m16.load_state_dict(W.make_state_dict(1234))
     m16 = m16.cuda().eval()
-    # clips of different loudness and spectra so that the random-init classifier does not answer one class for all
-    g = torch.Generator().manual_seed(11)
-    base = W.make_waveforms(512, 16000, seed=21)
-    tt = torch.arange(16000) / 16000.0
-    tone = torch.sin(2 * torch.pi * (100 + 3000 * torch.rand(512, 1, 1, generator=g)) * tt)
-    x = ((0.1 + 0.9 * torch.rand(512, 1, 1, generator=g)) * (0.5 * base + 0.5 * tone)).clamp(-1, 1).cuda()
+    x = W.make_clips(512, 16000, seed=21).cuda()
     outs = []
     for model in (m16, full_model):
         dw = ap.DiffWave(model, hp, reverse_timestep=2, seed=77)
@@ -235,4 +240,4 @@ def test_top1_agreement_bf16_vs_tf32_on_512_clips(full_model, hp):
     agree = float((l16.argmax(1) == l32.argmax(1)).float().mean())
     assert agree >= 0.995, agree
     assert rel_l2(l16, l32) < 1e-2
-    assert len(torch.unique(l32.argmax(1))) > 1  # the check is not vacuous
+    assert len(torch.unique(l32.argmax(1))) >= 5  # the check is not vacuous

@@ -146,9 +146,10 @@ def test_sde_matches_affine_form(eps_fn):
 def test_log_mel(golden):
     g = golden("mel.npz")
     np.testing.assert_allclose(mel.melscale_fbanks().numpy(), g["fb"], rtol=0, atol=0)
-    x = torch.cat([W.make_waveforms(2, 16000, seed=0), torch.from_numpy(golden("ddpm_t2.npz")["purified"])], 0)
+    x = torch.cat([W.make_waveforms(2, 16000, seed=0), torch.from_numpy(golden("ddpm_t2.npz")["purified"]),
+                   W.make_clips(4, 16000, seed=20)], 0)
     db = mel.log_mel(x)
-    assert db.shape == (4, 1, 32, 32)
+    assert db.shape == (8, 1, 32, 32)
     assert float((db - torch.from_numpy(g["logmel"])).abs().max()) < 1e-3
     # independent float64 framing + rfft agrees to fp32 rounding
     assert float(np.abs(mel.log_mel_f64(x) - g["logmel"]).max()) < 2e-3
@@ -158,31 +159,108 @@ def test_resnext_and_acoustic_system(golden, hp, eps_fn):
     csd = resnext.make_state_dict(4321)
     spec = torch.from_numpy(golden("mel.npz")["logmel"])
     logits = resnext.forward(csd, spec)
-    assert rel_l2(logits, golden("resnext.npz")["logits"]) < 1e-5
+    want = golden("resnext.npz")["logits"]
+    assert rel_l2(logits, want) < 1e-5
+    assert len(set(want.argmax(1).tolist())) >= 3          # the calibrated checkpoint separates its inputs
     g = golden("acoustic.npz")
-    x = W.make_waveforms(2, 16000, seed=0)
+    x = W.make_clips(2, 16000, seed=int(g["x_seed"]))
     nodef = resnext.forward(csd, mel.log_mel(x))
     assert rel_l2(nodef, g["logits_nodefend"]) < 1e-4
-    z = W.make_noise((2, 2, 1, 16000), seed=7)
+    z = W.make_noise((2, 2, 1, 16000), seed=int(g["z_seed"]))
     y = purify.ddpm_purify(hp, eps_fn, x, 2, z)
     out = resnext.forward(csd, mel.log_mel(y))
     assert rel_l2(out, g["logits"]) < 1e-4
     assert np.array_equal(out.argmax(1).numpy(), g["logits"].argmax(1))
 
 
-def test_smooth_predict_counts(golden, hp, eps_fn):
-    g = golden("smooth.npz")
+def test_calibrated_classifier_is_not_degenerate():
+    """The round-1 synthetic checkpoint predicted one class for every input, which made every top-1 / vote
+    comparison vacuous.  The calibrated one must spread 256 synthetic clips over >= 5 classes with near-ties."""
     csd = resnext.make_state_dict(4321)
-    x = W.make_waveforms(1, 16000, seed=0)[0]
-    z = W.make_noise((6, 1, 16000), seed=int(g["z_seed"]))
-    sigma = float(g["sigma"])
+    logits = resnext.forward(csd, mel.log_mel(W.make_clips(64, 16000, seed=31)))
+    assert len(set(logits.argmax(1).tolist())) >= 5
+    raw = resnext.forward(resnext.make_state_dict(4321, calibrated=False), mel.log_mel(W.make_clips(8, 16000, seed=31)))
+    assert len(set(raw.argmax(1).tolist())) == 1           # documents why calibration is needed
+
+
+def test_pipeline_fixture_first_clips(golden, hp, eps_fn):
+    """pipeline256.npz (reference AcousticSystem on 256 structured clips): the oracle reproduces its first two
+    clips (logits and sampled purified waveform); the fixture itself spans >= 5 classes with near-ties."""
+    g = golden("pipeline256.npz")
+    want = g["logits"]
+    assert want.shape == (256, 10) and len(set(want.argmax(1).tolist())) >= 5
+    top2 = np.sort(want, 1)[:, -2:]
+    assert int(((top2[:, 1] - top2[:, 0]) < 0.05).sum()) >= 2
+    n = 2
+    x = W.make_clips(256, 16000, seed=int(g["x_seed"]))[:n]
+    z = W.make_noise((2, 256, 1, 16000), seed=int(g["z_seed"]))[:, :n]
+    y = purify.ddpm_purify(hp, eps_fn, x, 2, z)
+    assert rel_l2(y[:, 0, torch.from_numpy(g["sample_idx"])], g["purified_samples"][:n]) < 1e-6
+    out = resnext.forward(resnext.make_state_dict(4321), mel.log_mel(y))
+    assert rel_l2(out, want[:n]) < 1e-4
+
+
+def test_one_shot_at_the_certifier_sigmas(golden, hp, eps_fn):
+    g = golden("oneshot_sigmas.npz")
+    x = W.make_clips(1, 16000, seed=int(g["x_seed"]))
+    z = W.make_noise((1, 1, 16000), seed=int(g["z_seed"]))
+    for sigma, t_star in zip(g["sigmas"], g["t_stars"]):
+        ab, t = schedule.compute_t_star(hp["Alpha_bar"], float(sigma))
+        assert t == int(t_star)
+        got = purify.one_shot_denoise(hp, eps_fn, ab ** 0.5 * (x + float(sigma) * z), t)
+        assert rel_l2(got, g["x0_hat_t%d" % t]) < 1e-6
+
+
+def test_sde_purify_t5(golden, eps_fn):
+    """sde_t5.npz: Euler-Maruyama driven by the reference's own RevVPSDE.f/.g, t = 5, B = 2."""
+    g = golden("sde_t5.npz")
+    t = int(g["t"])
+    x = W.make_clips(2, 16000, seed=int(g["x_seed"]))
+    z = W.make_noise((t + 1, 2, 1, 16000), seed=int(g["z_seed"]))
+    got = purify.sde_purify(schedule.sde_tables(), eps_fn, x, t, z[0], z[1:].reshape(t, 2, 16000))
+    assert rel_l2(got, g["purified"]) < 1e-6
+
+
+def test_certify_fixture(golden, hp, eps_fn):
+    """certify.npz: the reference's RobustCertificate.certify on two clips (n_0 = 32, n = 128).  Integer work on the
+    reference's own logits is bit-exact; the oracle's logits match on a sample of draws; certify_from_counts gives the
+    reference's (class, radius), including the abstention."""
+    g = golden("certify.npz")
+    n_0, n, sigma = int(g["n_0"]), int(g["n"]), float(g["sigma"])
+    logits = torch.from_numpy(g["logits"])                                 # (2, n_0 + n, 10)
     assert schedule.compute_t_star(hp["Alpha_bar"], sigma)[1] == int(g["t_star"])
-    logits = torch.cat([certify.smooth_logits(hp, eps_fn, mel.log_mel, lambda s: resnext.forward(csd, s), x, z[s:s + 4], sigma)
-                        for s in (0, 4)], 0)
-    assert rel_l2(logits, g["logits"]) < 1e-4
-    counts = certify.vote_counts(logits, 10)
-    assert counts.dtype == torch.int64
-    assert np.array_equal(counts.numpy(), g["counts"])  # integer work: bit-exact
+    outcomes = set()
+    for i in range(logits.shape[0]):
+        c0 = certify.vote_counts(logits[i, :n_0], 10)
+        c = certify.vote_counts(logits[i, n_0:], 10)
+        assert np.array_equal(c0.numpy(), g["counts_0"][i]) and np.array_equal(c.numpy(), g["counts"][i])
+        cls, r = certify.certify_from_counts(c0, c, n, sigma, float(g["alpha"]))
+        assert cls == int(g["y_pred"][i]) and abs(r - float(g["radius"][i])) < 1e-6
+        outcomes.add(cls)
+        assert int((c > 0).sum()) >= 2                                    # multi-class vote histograms
+    assert -1 in outcomes and len(outcomes) == 2                           # one certified clip, one abstention
+    csd = resnext.make_state_dict(4321)
+    x = W.make_clips(8, 16000, seed=int(g["x_seed"]))[g["clips"]]
+    z = W.make_noise((2, n_0 + n, 1, 16000), seed=int(g["z_seed"]))
+    draws = [0, n_0, n_0 + n - 1]
+    for i in (0, 1):
+        got = certify.smooth_logits(hp, eps_fn, mel.log_mel, lambda s: resnext.forward(csd, s), x[i], z[i, draws], sigma)
+        assert rel_l2(got, logits[i, draws]) < 1e-4
+
+
+def test_nes_eot_restatement(golden):
+    from oracle import blackbox
+
+    g = golden("nes.npz")
+    N, spd, S = int(g["N"]), int(g["samples_per_draw"]), int(g["samples_per_draw_batch"])
+    x = W.make_clips(3, N, seed=int(g["x_seed"]))
+    z = W.make_noise((spd // S, 3, S // 2, 1, N), seed=int(g["z_seed"]))
+    loss = torch.nn.CrossEntropyLoss(reduction="none")
+    out = blackbox.nes(blackbox.toy_model(N, seed=int(g["model_seed"])), loss, x, torch.from_numpy(g["y"]), z, spd, S,
+                       float(g["sigma"]), int(g["EOT_size"]), int(g["EOT_batch_size"]))
+    for got, key in zip(out[:4], ("mean_loss", "grad", "adver_loss", "adver_score")):
+        assert rel_l2(got, g[key]) < 1e-6, key
+    assert np.array_equal(out[4], g["predict"])
 
 
 def test_clopper_pearson_known_answers():

@@ -116,4 +116,5 @@ def test_product_synthetic_checkpoints_equal_oracle_ones():
     a, b = S.resnext_state_dict(4321), o_resnext.make_state_dict(4321)
     assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
     assert torch.equal(S.waveforms(3, 1000, seed=5), W.make_waveforms(3, 1000, seed=5))
+    assert torch.equal(S.clips(3, 1000, seed=5), W.make_clips(3, 1000, seed=5))
     assert torch.equal(S.noise((2, 3, 4), seed=9), W.make_noise((2, 3, 4), seed=9))

@@ -39,21 +39,24 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False, ablation=False):
+def build(force=False, verbose=False, ablation=False, out=None, defines=()):
     """Compile if missing or older than its sources. Returns the library path.
-    ablation=True adds -DAP_ENABLE_ABLATION (the AP_DEBUG switches used for profiles/r01_ablation.md)."""
-    if not force and not stale():
+    ablation=True adds -DAP_ENABLE_ABLATION (the AP_DEBUG switches used for profiles/r0*_ablation.md).
+    out / defines: build a VARIANT library next to the product one (A/B experiments, selected with AP_LIB=...)."""
+    lib = os.path.join(HERE, out) if out else LIB
+    if not force and not out and not stale():
         return LIB
     cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DAP_ENABLE_ABLATION"] if ablation else [])
-           + ["-o", LIB] + SOURCES + LINK)
+           + ["-D" + d for d in defines] + ["-o", lib] + SOURCES + LINK)
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
     if verbose:
         print(proc.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
     print(build(force="--force" in sys.argv or "--ablation" in sys.argv, verbose="-v" in sys.argv,
-                ablation="--ablation" in sys.argv))
+                ablation="--ablation" in sys.argv, out=_out, defines=[a[2:] for a in sys.argv if a.startswith("-D")]))

@@ -30,6 +30,20 @@ def shard_range(n, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def work_batches(n_clips, per_clip, rank, world_size, batch_size):
+    """The launch plan of one certify call on one rank: the clip-major work list of ``n_clips * per_clip``
+    (clip, draw) items is split contiguously over the ranks (``shard_range``), and this rank's slice is cut into
+    full batches -- which may span clips -- plus at most one ragged batch.  Yields (first flat item, rows)."""
+    lo, hi = shard_range(n_clips * per_clip, rank, world_size)
+    for s in range(lo, hi, batch_size):
+        yield s, min(batch_size, hi - s)
+
+
+def flat_to_clip_draw(flat, per_clip, first_draw=0):
+    """(clip, draw index) of work item ``flat`` -- the rule the kernels apply (csrc smooth_inputs_kernel)."""
+    return flat // per_clip, first_draw + flat % per_clip
+
+
 class NcclCountsAllReduce:
     """Sums int64 device counters over ranks with ``ap_allreduce_counts``.  The NCCL unique id is created on
     rank 0 and shipped through an already-initialised ``torch.distributed`` group (any backend); a 1-rank
@@ -136,12 +150,10 @@ class RobustCertificate():
         if z is not None:
             z = z.to(device=x.device, dtype=torch.float32).contiguous()
             assert z.numel() == C * per_clip * L, "injected noise must be (clips, draws, 1, L)"
-        lo, hi = shard_range(C * per_clip, self.rank, self.world_size)
         if self._x_in is None or self._x_in.shape != (batch_size, 1, L) or self._x_in.device != x.device:
             self._x_in = torch.empty(batch_size, 1, L, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            for s in range(lo, hi, batch_size):
-                b = min(batch_size, hi - s)
+            for s, b in work_batches(C, per_clip, self.rank, self.world_size, batch_size):
                 x_in = self._x_in[:b]
                 _lib.check(lib.ap_smooth_inputs_batch(x.data_ptr(), L, b, s, per_clip, first_draw, float(sigma),
                                                       float(scale), z.data_ptr() if z is not None else None,

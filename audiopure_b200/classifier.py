@@ -139,7 +139,9 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
 class FusedResNeXt(nn.Module):
     """Inference form of a trained/loaded ``CifarResNeXt``: batch-norms folded into the
     convolutions, channels-last, bf16 weights and activations with fp32 accumulation (cuDNN), fp32 logits.
-    ``FusedResNeXt(clf)`` is a drop-in for ``clf.eval()`` in the ``classifier`` slot; it removes the 31 batch-norm
+    ``FusedResNeXt(clf)`` stands in for ``clf.eval()`` in the ``classifier`` slot for INFERENCE ONLY (evaluation,
+    certification, black-box queries): it has no backward pass and raises if its input requires grad -- keep the
+    plain module for attacks that back-propagate through ``AcousticSystem``.  It removes the 31 batch-norm
     and ~50 layout-conversion launches per batch that the reference module issues, and applies bias, residual add
     and ReLU in one in-place pass per convolution (``ap_bias_act_nhwc_bf16``)."""
 
@@ -156,8 +158,16 @@ class FusedResNeXt(nn.Module):
         for conv in [m for m in self.modules() if isinstance(m, nn.Conv2d)]:
             conv.to(dtype)  # the fp32 bias buffers of the fused epilogue are left alone
 
-    @torch.no_grad()
     def forward(self, x):
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError(
+                "FusedResNeXt is inference-only (in-place bf16 epilogue kernels, no autograd): an input that requires "
+                "grad would silently lose its gradient here.  Use the plain CifarResNeXt module in the classifier slot "
+                "when back-propagating through AcousticSystem (adaptive attacks).")
+        with torch.no_grad():
+            return self._forward(x)
+
+    def _forward(self, x):
         x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
         x = _bias_act(_conv_nobias(self.stem, x), self.b_stem)
         x = self.blocks(x)

@@ -111,10 +111,16 @@ struct ap_net {
   std::vector<float> alpha, alpha_bar, sigma, sde_beta, sde_acp;
   CUtensorMap tm_w1, tm_w2, tm_ws, tm_wf;
   int num_sms = 0, device = 0;
-  // activation maps, rebuilt when (workspace, Bc, L) changes
-  const void* cached_ws = nullptr;
-  int cached_B = 0, cached_L = 0;
-  CUtensorMap tm_h[2], tm_h_st[2], tm_gate, tm_gate_st;  // loads use [128-row] boxes, epilogue stores [32-row]
+  // activation maps for one (workspace, Bc, L); two sets are cached so that a batch that is not a multiple of
+  // max_chunk (a full chunk and a remainder chunk alternate on every evaluation) re-encodes nothing
+  struct ActMaps {
+    const void* ws = nullptr;
+    int B = 0, L = 0;
+    uint64_t last_use = 0;
+    CUtensorMap tm_h[2], tm_h_st[2], tm_gate, tm_gate_st;  // loads use [128-row] boxes, epilogue stores [32-row]
+  };
+  ActMaps maps[2];
+  uint64_t map_clock = 0;
   // measurement hook (ap_profile_*)
   bool profile = false;
   struct Span {
@@ -181,29 +187,42 @@ WsLayout ws_layout(const ap_net* n, int Bc, int L) {
   return w;
 }
 
-int ensure_maps(ap_net* n, uint8_t* ws, int Bc, int L) {
-  if (n->cached_ws == ws && n->cached_B == Bc && n->cached_L == L) return 0;
+int ensure_maps(ap_net* n, uint8_t* ws, int Bc, int L, const ap_net::ActMaps** out) {
+  ap_net::ActMaps* victim = &n->maps[0];
+  for (auto& m : n->maps) {
+    if (m.ws == ws && m.B == Bc && m.L == L) {
+      m.last_use = ++n->map_clock;
+      *out = &m;
+      return 0;
+    }
+    if (m.last_use < victim->last_use) victim = &m;
+  }
+  ap_net::ActMaps& m = *victim;
+  m.ws = nullptr;  // invalid until every map below is encoded
   const WsLayout w = ws_layout(n, Bc, L);
   const uint64_t d3[3] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc)};
   for (int i = 0; i < 2; ++i)
-    if (make_map(&n->tm_h[i], ws + w.off_h[i], 3, d3, ap::kTileT, n->tf32) ||
-        make_map(&n->tm_h_st[i], ws + w.off_h[i], 3, d3, 32, n->tf32))
+    if (make_map(&m.tm_h[i], ws + w.off_h[i], 3, d3, ap::kTileT, n->tf32) ||
+        make_map(&m.tm_h_st[i], ws + w.off_h[i], 3, d3, 32, n->tf32))
       return 1;
   const uint64_t d4[4] = {static_cast<uint64_t>(ap::kC), static_cast<uint64_t>(L), static_cast<uint64_t>(Bc),
                           static_cast<uint64_t>(n->layers)};
-  if (make_map(&n->tm_gate, ws + w.off_gate, 4, d4, ap::kTileT, n->tf32) ||
-      make_map(&n->tm_gate_st, ws + w.off_gate, 4, d4, 32, n->tf32))
+  if (make_map(&m.tm_gate, ws + w.off_gate, 4, d4, ap::kTileT, n->tf32) ||
+      make_map(&m.tm_gate_st, ws + w.off_gate, 4, d4, 32, n->tf32))
     return 1;
-  n->cached_ws = ws;
-  n->cached_B = Bc;
-  n->cached_L = L;
+  m.ws = ws;
+  m.B = Bc;
+  m.L = L;
+  m.last_use = ++n->map_clock;
+  *out = &m;
   return 0;
 }
 
 // One epsilon-network evaluation of Bc clips (+ the fused output update described by `tail`).
 int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail, uint8_t* ws, cudaStream_t st) {
   AP_CHECK(t >= 0 && t < n->T, "diffusion step t out of range [0, T)");
-  if (ensure_maps(n, ws, Bc, L)) return 1;
+  const ap_net::ActMaps* mp = nullptr;
+  if (ensure_maps(n, ws, Bc, L, &mp)) return 1;
   const WsLayout w = ws_layout(n, Bc, L);
   void* h0 = ws + w.off_h[0];
   const long long rows = static_cast<long long>(Bc) * L;
@@ -259,12 +278,12 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
     ProfSpan span(n, st, 0);
     if (n->tf32) {
       lc.dynamicSmemBytes = ap::Mode<true>::kLayerSmem;
-      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<true>, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
-                                 n->tm_h_st[(l + 1) & 1], bias, a));
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<true>, mp->tm_h[l & 1], n->tm_w1, n->tm_w2, mp->tm_gate_st,
+                                 mp->tm_h_st[(l + 1) & 1], bias, a));
     } else {
       lc.dynamicSmemBytes = ap::Mode<false>::kLayerSmem;
-      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<false>, n->tm_h[l & 1], n->tm_w1, n->tm_w2, n->tm_gate_st,
-                                 n->tm_h_st[(l + 1) & 1], bias, a));
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::layer_kernel<false>, mp->tm_h[l & 1], n->tm_w1, n->tm_w2, mp->tm_gate_st,
+                                 mp->tm_h_st[(l + 1) & 1], bias, a));
     }
   }
   tail.bo = n->w.bo;
@@ -278,10 +297,10 @@ int run_eval(ap_net* n, const float* x, int Bc, int L, int t, ap::TailArgs tail,
     ProfSpan span(n, st, 1);
     if (n->tf32) {
       lc.dynamicSmemBytes = ap::Mode<true>::kTailSmem;
-      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<true>, n->tm_gate, n->tm_ws, n->tm_wf, n->tail_bias, tail));
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<true>, mp->tm_gate, n->tm_ws, n->tm_wf, n->tail_bias, tail));
     } else {
       lc.dynamicSmemBytes = ap::Mode<false>::kTailSmem;
-      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<false>, n->tm_gate, n->tm_ws, n->tm_wf, n->tail_bias, tail));
+      AP_CUDA(cudaLaunchKernelEx(&lc, ap::tail_kernel<false>, mp->tm_gate, n->tm_ws, n->tm_wf, n->tail_bias, tail));
     }
   }
   AP_CUDA(cudaGetLastError());

@@ -272,7 +272,8 @@ __device__ __forceinline__ uint32_t live_tap_mask(int unit, int num_tiles, int t
 //   GEMM1  D1[128 x 512] = sum_{tap,c} h[l + (tap-1)d][c] * W1[o][c][tap]     (K = 768)
 //          issued as two N = 256 chunks; chunk c holds gate channels [128c, 128c+128): TMEM columns
 //          [0,128) are their tanh rows, [128,256) their sigmoid rows (W1 rows are permuted at pack time).
-//   gate   g = tanh(D1t + b) * sigmoid(D1s + b)  -> bf16 -> shared memory (K-major, SW128) AND, by TMA
+//   gate   g = tanh(D1t + b) * sigmoid(2 (D1s + b))   (sigmoid rows are packed pre-halved, see gate_act)
+//          -> bf16 -> shared memory (K-major, SW128) AND, by TMA
 //          store from that same shared tile, to gate[layer] in HBM for the tail's skip GEMM.
 //   GEMM2  D2[128 x 256] = g * (sqrt(.5) W_res)^T                                  (K = 256)
 //   out    h_next = sqrt(.5) * h + D2 + (sqrt(.5) b_res + part_{n+1})   (the residual term is the shifted
@@ -289,11 +290,19 @@ __device__ __forceinline__ uint32_t live_tap_mask(int unit, int num_tiles, int t
 // and stores its own [32 x 64] boxes, so the eight warps never need a CTA-wide barrier.  (Per-thread 16-byte
 // global accesses at a 512-byte stride cost 0.91 -> 0.56 ms per launch in an ablation; see profiles/.)
 // ---------------------------------------------------------------------------------------------------
+// Ablation switches (AP_DEBUG env; profiles/r01_ablation.md, r02_ablation.md) change results and exist only in builds
+// made with -DAP_ENABLE_ABLATION (python -m audiopure_b200.build --ablation); the product library compiles them out.
+#ifdef AP_ENABLE_ABLATION
+#define AP_ABL(args, bit) (((args).debug & (bit)) != 0)
+#else
+#define AP_ABL(args, bit) false
+#endif
+
 struct LayerArgs {
   int L, tiles_per_clip, num_tiles;
   int dilation, layer;
   int write_h;  // 0 for the last layer (its residual output is never consumed)
-  int debug;    // ablation switches (AP_DEBUG env, profiles/r01_ablation.md): 2 no MUFU, 4 no h_next store, 8 no gate store
+  int debug;    // ablation switches: 2 no MUFU, 4 no h_next store, 8 no gate store, 16 chunk 1 re-uses stale activation stages (no second A stream)
   uint32_t round_bias;  // tf32 only: see tile_store32
 };
 struct LayerBias {  // passed by value: lives in the constant bank, read with warp-uniform indices
@@ -376,9 +385,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
           const int s = it % kStages;
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1, 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx_cluster(full0 + 8 * s, T::kStageBytes);
+            const bool skip_a = AP_ABL(a, 16) && c == 1;  // timing bound only: chunk 1 multiplies whatever the stage holds
+            mbar_arrive_expect_tx_cluster(full0 + 8 * s, skip_a ? T::kBBytes : T::kStageBytes);
             uint8_t* sa = stage_base + s * T::kStageBytes;
-            tma_load_3d_pair(sa, &tm_h, full0 + 8 * s, (ks % kSubs) * kSubK, tc.l0 + (tap - 1) * a.dilation, tc.b);
+            if (!skip_a)
+              tma_load_3d_pair(sa, &tm_h, full0 + 8 * s, (ks % kSubs) * kSubK, tc.l0 + (tap - 1) * a.dilation, tc.b);
             tma_load_2d_pair(sa + kABytes, &tm_w1, full0 + 8 * s, ks * kSubK, a.layer * 512 + c * 256 + brow);
           }
           __syncwarp();
@@ -505,7 +516,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
           const float* bt = bias.b1 + c * 256 + j0;
           const float* bs = bt + 128;
           float o[32];
-          if (a.debug & 2) {
+          if (AP_ABL(a, 2)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(rt[j]) + bt[j] + __uint_as_float(rs[j]) + bs[j];
           } else {
@@ -521,7 +532,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         if (lane == 0) {
           mbar_arrive_cluster(gate_ready0 + 8 * c);
           // this warp's [32 x 64-channel] part of the gate tile -> HBM (operand of the tail's skip GEMM)
-          if (!(a.debug & 8)) {
+          if (!AP_ABL(a, 8)) {
 #pragma unroll
             for (int s = 0; s < T::kSubsPer64; ++s) {
               const int sub = (2 * c + hh) * T::kSubsPer64 + s;
@@ -567,7 +578,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && a.write_h && !(a.debug & 4)) {
+      if (lane == 0 && a.write_h && !AP_ABL(a, 4)) {
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk)
 #pragma unroll

@@ -15,7 +15,7 @@
 namespace ap {
 
 #ifndef AP_WATCHDOG
-#define AP_WATCHDOG 1  // bounded mbarrier spins: a protocol bug traps instead of hanging the GPU
+#define AP_WATCHDOG 1  // 1: bounded mbarrier spins, a protocol bug traps instead of hanging the GPU; 2: and says where
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -53,8 +53,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 24)) {
+#if AP_WATCHDOG >= 2
       printf("audiopure_b200: mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);
+#endif
       __trap();
     }
   }
@@ -329,15 +331,24 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-// TF32 mode: tanh.approx (2^-11 relative) would be the largest error left, so use fp32-accurate forms there.
-__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// The sigmoid rows of the packed dilated-conv weights and bias carry a factor 1/2 (exact in bf16 / tf32, folded in
+// at pack time), so the GEMM delivers s_half = s / 2 and sigmoid(s) = 1/2 tanh(s_half) + 1/2 costs one MUFU + one FMA.
+#ifdef AP_AB_NO_FOLD  // timing-only A/B variant (profiles/r02_ablation.md): the round-1 epilogue's extra multiply
+__device__ __forceinline__ float sigmoid_fast_half(float s_half) { return fmaf(0.5f, tanh_fast(0.5f * s_half), 0.5f); }
+#else
+__device__ __forceinline__ float sigmoid_fast_half(float s_half) { return fmaf(0.5f, tanh_fast(s_half), 0.5f); }
+#endif
+// TF32 mode: tanh.approx (2^-11 relative) would be the largest error left, so use fp32-accurate forms there:
+// 1 / (1 + exp(-2 s_half)), the factor 2 folded into the exp2 scaling.
+__device__ __forceinline__ float sigmoid_acc_half(float s_half) {
+  return __fdividef(1.0f, 1.0f + exp2f(-2.8853900817779268f * s_half));
+}
 template <bool kAccurate>
-__device__ __forceinline__ float gate_act(float t, float s) {
+__device__ __forceinline__ float gate_act(float t, float s_half) {
   if constexpr (kAccurate)
-    return tanhf(t) * sigmoid_acc(s);
+    return tanhf(t) * sigmoid_acc_half(s_half);
   else
-    return tanh_fast(t) * sigmoid_fast(s);
+    return tanh_fast(t) * sigmoid_fast_half(s_half);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

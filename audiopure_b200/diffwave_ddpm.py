@@ -19,6 +19,16 @@ from .schedule import calc_diffusion_hyperparams
 from .wavenet import WaveNet_Speech_Commands
 
 
+def default_seed():
+    """Philox seed when the caller gives none: torch's global seed (so ``torch.manual_seed`` governs the purifier's
+    noise as it governs the reference's ``torch.normal`` draws), mixed with the rank when ``torch.distributed`` is
+    initialised so that ranks of one job do not purify with identical noise."""
+    seed = torch.initial_seed()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed ^= (torch.distributed.get_rank() + 1) * 0x9E3779B97F4A7C15
+    return seed & 0xFFFFFFFFFFFFFFFF
+
+
 def _as_tensor(x):
     if isinstance(x, np.ndarray):  # diffwave_ddpm.py:38-39,52-53,78-79
         x = torch.from_numpy(x)
@@ -28,14 +38,14 @@ def _as_tensor(x):
 class DiffWave(torch.nn.Module):
 
     def __init__(self, model: WaveNet_Speech_Commands, diffusion_hyperparams: dict, reverse_timestep: int = 200,
-                 grad_enable=True, seed: int = 0):
+                 grad_enable=True, seed: int = None):
         super().__init__()
         self.model = model
         self.diffusion_hyperparams = diffusion_hyperparams
         self.reverse_timestep = reverse_timestep
         self.freeze = False
         self.grad_enable = grad_enable
-        self.seed = seed
+        self.seed = default_seed() if seed is None else seed
         self._calls = 0
         self._check_tables()
 

@@ -16,7 +16,7 @@ add a degenerate zero-length step at some t -- SURVEY.md section 7 -- which is n
 import numpy as np
 import torch
 
-from .diffwave_ddpm import DiffWave, create_diffwave_model
+from .diffwave_ddpm import DiffWave, create_diffwave_model, default_seed
 from .schedule import sde_tables
 
 
@@ -97,7 +97,7 @@ class RevDiffWave(torch.nn.Module):
     "bf16" | "tf32").  A ready ``DiffWave`` may be
     passed as ``model=`` instead of a checkpoint path."""
 
-    def __init__(self, args, device=None, model: DiffWave = None, seed: int = 0):
+    def __init__(self, args, device=None, model: DiffWave = None, seed: int = None):
         super().__init__()
         self.args = args
         if device is None:
@@ -115,7 +115,7 @@ class RevDiffWave(torch.nn.Module):
                                   beta_min=0.0001 * self.T, beta_max=0.02 * self.T, N=self.T,
                                   audio_shape=audio_shape, model_kwargs=None)
         self.betas = self.rev_vpsde.discrete_betas.float().to(self.device)
-        self.seed = seed
+        self.seed = default_seed() if seed is None else seed
         self._calls = 0
 
     def audio_editing_sample(self, audio, z: torch.Tensor = None, clip_offset: int = 0):

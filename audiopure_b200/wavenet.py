@@ -140,6 +140,11 @@ class WaveNet_Speech_Commands(nn.Module):
         # first their tanh rows (conv out channels 128c..), then their sigmoid rows (256+128c..)  (WaveNet.py:90)
         perm = torch.cat([torch.arange(128) + 128 * c + 256 * half for c in range(2) for half in range(2)]).to(dev)
 
+        # the sigmoid rows carry a factor 1/2 (exact in bf16 / tf32): sigmoid(s) = 1/2 tanh(s/2) + 1/2 then needs no
+        # multiply in the epilogue (csrc/sm100.cuh gate_act)
+        half = torch.ones(512, 1, **f32)
+        half[128:256] = 0.5
+        half[384:512] = 0.5
         w1 = torch.empty(L, 512, 768, **f32)
         b1 = torch.empty(L, 512, **f32)
         w2 = torch.empty(L, 256, 256, **f32)
@@ -150,8 +155,8 @@ class WaveNet_Speech_Commands(nn.Module):
         for n, blk in enumerate(blocks):
             w, b = blk.dilated_conv_layer.conv.folded()          # (512, 256, 3)
             w = w.to(dev).permute(0, 2, 1).reshape(512, 768)     # K index = tap*256 + cin
-            w1[n] = w[perm]
-            b1[n] = b.to(dev)[perm]
+            w1[n] = w[perm] * half
+            b1[n] = b.to(dev)[perm] * half[:, 0]
             wr, br = blk.res_conv.folded()
             w2[n] = wr.to(dev)[:, :, 0] * math.sqrt(0.5)         # WaveNet.py:97
             b_res[n] = br.to(dev)

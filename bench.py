@@ -229,6 +229,9 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
     class TimedAllReduce(NcclCountsAllReduce):
         calls, bytes, spans = 0, 0, []
 
+        def reset(self):
+            self.calls, self.bytes, self.spans = 0, 0, []
+
         def __call__(self, counts):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -252,7 +255,7 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
         return RC.certify(x, y, sigma=sigma, n_0=n0, n=n, batch_size=bs, clip_offset=0)
 
     run()  # warm-up with exactly the timed call's batch shapes (cuDNN autotunes per shape, ragged last batch included)
-    TimedAllReduce.calls, TimedAllReduce.bytes, TimedAllReduce.spans = 0, 0, []
+    allreduce.reset()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -267,7 +270,7 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    coll_ms = sum(a.elapsed_time(b) for a, b in TimedAllReduce.spans)
+    coll_ms = sum(a.elapsed_time(b) for a, b in allreduce.spans)
     counts_0, counts = RC.last_counts
     certify = {
         "workload": "BASELINE configs[3]: %d clips x (n_0 = %d + n = %d) smoothing draws, sigma = %.2f (t* = 34): "
@@ -278,8 +281,8 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
         "y_pred": y_pred.tolist(), "radius": [round(float(r), 4) for r in radius.tolist()],
         "counts_checksum": int((counts * torch.arange(1, 11)).sum() + 31 * (counts_0 * torch.arange(1, 11)).sum()),
     }
-    collective = {"name": "ncclAllReduce int64 sum (ap_allreduce_counts, NCCL via dlopen)", "calls": TimedAllReduce.calls,
-                  "bytes": TimedAllReduce.bytes, "ms": coll_ms, "nranks": world,
+    collective = {"name": "ncclAllReduce int64 sum (ap_allreduce_counts, NCCL via dlopen)", "calls": allreduce.calls,
+                  "bytes": allreduce.bytes, "ms": coll_ms, "nranks": world,
                   "where": "inside the certify timed region, once per certify call"}
     return certify, collective
 

@@ -58,8 +58,8 @@ typedef struct ap_config {
 /* Packed weights, DEVICE pointers that must outlive the handle (WaveNet_Speech_Commands.pack_weights in audiopure_b200/wavenet.py builds them from
  * a reference-layout state dict: weight-norm folded once, WaveNet.py:28,67,72).                   */
 typedef struct ap_weights {
-  const void* w1;     /* bf16 (fp32 with AP_FLAG_TF32, also w2/ws/wf) [layers][512][768]: dilated conv, rows gate-interleaved, K = tap*256 + cin   */
-  const float* b1;    /* f32  [layers][512]: its bias, same row order                                      */
+  const void* w1;     /* bf16 (fp32 with AP_FLAG_TF32, also w2/ws/wf) [layers][512][768]: dilated conv, rows gate-interleaved (sigmoid rows x 1/2), K = tap*256 + cin */
+  const float* b1;    /* f32  [layers][512]: its bias, same row order and 1/2 factors                       */
   const void* w2;     /* bf16 [layers][256][256]: sqrt(.5) * res_conv                                      */
   const float* c2;    /* f32  [T][layers][256]: sqrt(.5)*b_res[n] + fc_t[n+1](emb(t))  (0 shift for last)  */
   const float* part0; /* f32  [T][256]: fc_t[0](emb(t))                                                    */

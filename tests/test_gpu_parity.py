@@ -408,10 +408,11 @@ def test_philox_normal_moments():
 # ------------------------------------------------------------------------------------------- front-end --
 def test_logmel_vs_torchaudio_fixture(golden):
     g = golden("mel.npz")
-    x = torch.cat([W.make_waveforms(2, 16000, seed=0), torch.from_numpy(golden("ddpm_t2.npz")["purified"])], 0)
+    x = torch.cat([W.make_waveforms(2, 16000, seed=0), torch.from_numpy(golden("ddpm_t2.npz")["purified"]),
+                   W.make_clips(4, 16000, seed=20)], 0)
     tr = ap.LogMelSpectrogram().cuda()
     got = tr(x.cuda())
-    assert got.shape == (4, 1, 32, 32)
+    assert got.shape == (8, 1, 32, 32)
     assert float((got.cpu() - torch.from_numpy(g["logmel"])).abs().max()) < 2e-2
 
 

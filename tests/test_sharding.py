@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from audiopure_b200.certified_robust import shard_range, torch_counts_allreduce
+from audiopure_b200.certified_robust import flat_to_clip_draw, shard_range, torch_counts_allreduce, work_batches
 
 
 def test_shard_range_partitions_every_draw_once():
@@ -20,6 +20,29 @@ def test_shard_range_partitions_every_draw_once():
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
     assert shard_range(10000, 0, 8) == (0, 1250)  # 1250 draws per GPU at 8 GPUs
+
+
+def test_work_batches_cover_every_clip_draw_pair_once_with_full_batches():
+    """The certify work list (clips x (n_0 + n) draws, clip-major) over 1..8 ranks: every (clip, draw) pair lands in
+    exactly one batch of one rank, every batch but a rank's last is full, and the n_0 / n split is by draw index."""
+    for clips, n_0, n, bs in ((1, 100, 10000, 64), (4, 100, 10000, 64), (3, 5, 21, 8), (2, 32, 128, 64), (5, 1, 1, 7)):
+        per_clip = n_0 + n
+        for world in (1, 2, 3, 8):
+            seen = set()
+            for r in range(world):
+                batches = list(work_batches(clips, per_clip, r, world, bs))
+                assert all(b == bs for _, b in batches[:-1]) and all(0 < b <= bs for _, b in batches)
+                for s, b in batches:
+                    for flat in range(s, s + b):
+                        item = flat_to_clip_draw(flat, per_clip)
+                        assert item not in seen
+                        seen.add(item)
+            assert seen == {(c, d) for c in range(clips) for d in range(per_clip)}
+            sel = sum(1 for c, d in seen if d < n_0)
+            assert sel == clips * n_0
+    # 8 GPUs, BASELINE configs[3]: 1263 or 1262 draws per rank = 19 full batches + one of 47 / 46, instead of the
+    # 12-13-draw slivers a per-clip, per-pass split of n_0 = 100 gives
+    assert [b for _, b in work_batches(1, 10100, 0, 8, 64)][-1] == 1263 - 19 * 64
 
 
 def _worker(rank, world, port, n, ret):

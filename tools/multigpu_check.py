@@ -34,7 +34,7 @@ def main():
     clf.load_state_dict(S.resnext_state_dict(4321))
     clf = clf.cuda().eval()
     tr = ap.LogMelSpectrogram().cuda()
-    x = S.waveforms(1, 16000, seed=4)[0].cuda()
+    x = S.clips(1, 16000, seed=4)[0].cuda()
 
     n = 203
     allreduce = NcclCountsAllReduce(rank, world)
@@ -46,8 +46,20 @@ def main():
     ok1 = torch.equal(counts, whole)
     print("rank %d: sharded counts %s %s unsharded %s" % (rank, counts.tolist(), "==" if ok1 else "!=", whole.tolist()), flush=True)
 
+    # certify over several clips: the flattened (clip, draw) work list sharded over the ranks, ONE all-reduce
+    xs = S.clips(3, 16000, seed=14).cuda()
+    ys = torch.zeros(3, dtype=torch.long, device="cuda")
+    a = ap.RobustCertificate(clf, tr, dw, seed=3, rank=rank, world_size=world, allreduce=allreduce)
+    yp, rad = a.certify(xs, ys, n_0=20, n=143, batch_size=16)
+    b = ap.RobustCertificate(clf, tr, dw, seed=3)
+    yq, rbd = b.certify(xs, ys, n_0=20, n=143, batch_size=16)
+    ok1 = ok1 and torch.equal(a.last_counts[0], b.last_counts[0]) and torch.equal(a.last_counts[1], b.last_counts[1]) \
+        and torch.equal(yp, yq) and torch.equal(rad, rbd)
+    print("rank %d: sharded certify counts %s, y_pred %s radius %s; equal to unsharded: %s"
+          % (rank, a.last_counts[1].tolist(), yp.tolist(), [round(r, 4) for r in rad.tolist()], ok1), flush=True)
+
     B = 4 * world
-    xb = S.waveforms(B, 2048, seed=8).cuda()
+    xb = S.clips(B, 2048, seed=8).cuda()
     eng = model.engine()
     full = eng.ddpm_purify(xb, 3, seed=77)
     lo, hi = shard_range(B, rank, world)

@@ -606,7 +606,10 @@ int ap_logmel(const float* x, int B, int L, float* out, const ap_mel_tables* tab
   a.n_frames = 1 + L / ap::kHop;
   a.n_mels = tabs->n_mels;
   const int pairs = (a.n_frames + 1) / 2;
-  ap::logmel_kernel<<<B * pairs, ap::kMelThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  // persistent over (clip, frame pair) items: up to 7 CTAs of 128 threads per SM (register-resident FFT), so the
+  // 1024 items of a 64-clip batch are all resident at once on 148 SMs
+  ap::logmel_kernel<<<grid_for(static_cast<long long>(B) * pairs, 1, 7), ap::kFwdThreads, 0,
+                      static_cast<cudaStream_t>(stream)>>>(a);
   AP_CUDA(cudaGetLastError());
   return 0;
 }

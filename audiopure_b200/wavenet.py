@@ -118,9 +118,18 @@ class WaveNet_Speech_Commands(nn.Module):
         """Drop the packed weights (call after mutating parameters in place)."""
         self._engine = None
 
+    def _signature(self):
+        p = next(self.parameters())
+        return p.device, p.dtype, p.data_ptr()
+
     def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
+        # .to() / .cuda() / .float() re-home the parameters: the packed copies follow.  A no-op move (same device and
+        # dtype, e.g. RevDiffWave's `model.eval().to(device)` on a model that is already there) keeps them.
+        before = self._signature()
+        out = super()._apply(fn, *a, **k)
+        if self._signature() != before:
+            self._engine = None
+        return out
 
     def engine(self):
         if self._engine is None:

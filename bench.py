@@ -271,6 +271,18 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     coll_ms = sum(a.elapsed_time(b) for a, b in allreduce.spans)
+    calls, nbytes = allreduce.calls, allreduce.bytes
+    # the same collective again with the ranks already in step: its own latency, without the wait for the slowest rank
+    probe = torch.zeros(2, clips, 10, dtype=torch.int64, device=dev)
+    allreduce(probe)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    allreduce.reset()
+    for _ in range(10):
+        allreduce(probe)
+    torch.cuda.synchronize()
+    in_step_ms = sum(a.elapsed_time(b) for a, b in allreduce.spans) / 10
     counts_0, counts = RC.last_counts
     certify = {
         "workload": "BASELINE configs[3]: %d clips x (n_0 = %d + n = %d) smoothing draws, sigma = %.2f (t* = 34): "
@@ -281,9 +293,11 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
         "y_pred": y_pred.tolist(), "radius": [round(float(r), 4) for r in radius.tolist()],
         "counts_checksum": int((counts * torch.arange(1, 11)).sum() + 31 * (counts_0 * torch.arange(1, 11)).sum()),
     }
-    collective = {"name": "ncclAllReduce int64 sum (ap_allreduce_counts, NCCL via dlopen)", "calls": allreduce.calls,
-                  "bytes": allreduce.bytes, "ms": coll_ms, "nranks": world,
-                  "where": "inside the certify timed region, once per certify call"}
+    collective = {"name": "ncclAllReduce int64 sum (ap_allreduce_counts, NCCL via dlopen)", "calls": calls,
+                  "bytes": nbytes, "ms": coll_ms, "ms_ranks_in_step": in_step_ms, "nranks": world,
+                  "where": "inside the certify timed region, once per certify call; `ms` is this rank's device time "
+                           "across the call, which includes waiting for the slowest rank to arrive; "
+                           "`ms_ranks_in_step` is the same all-reduce repeated 10x with the ranks synchronised"}
     return certify, collective
 
 
@@ -394,7 +408,10 @@ def run_ours(args):
     layer_ms, layer_n = prof["layer"]
     chunks = (B + model.max_chunk - 1) // model.max_chunk
     evals_per_step = args.t_star * chunks
-    launches_per_step = chunks * (1 + args.t_star * (model.num_res_layers + 2)) + 1  # diffuse + evals; log-mel (ours)
+    # our kernels per step: per chunk the diffusion + t* x (prologue, 36 layers, tail); the log-mel kernel; and the
+    # consumer's fused bias/residual/ReLU epilogue (stem + 3 per bottleneck) when the bf16 classifier form is used
+    clf_launches = (1 + 3 * len(clf.blocks)) if args.classifier == "fused" else 0
+    launches_per_step = chunks * (1 + args.t_star * (model.num_res_layers + 2)) + 1 + clf_launches
     peak, peak_src = measured_peak()
     if args.precision == "tf32":  # no measured tf32 figure: the tensor core's tf32 rate is half its bf16 rate
         peak, peak_src = peak / 2, peak_src + " / 2 (tf32 = half the bf16 rate)"

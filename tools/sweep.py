@@ -107,6 +107,7 @@ def main():
                 ms_p = timed(purify, reps)
                 ms_f = timed(full, reps)
                 # second pass on this rank: per-kernel device time
+                eng = model.engine()
                 eng.profile(True)
                 eng.profile_read()
                 purify()

@@ -7,11 +7,16 @@ num_classes)``, ``certify``, ``smooth_predict``, ``compute_t_star``, ``lower_con
 * the smoothing noise is drawn on the device by a counter-based Philox keyed on (seed, clip, draw index,
   sample), fused with the ``x + delta`` and ``sqrt(alpha_bar*)`` scaling (certified_robust.py:46-54) -- the
   reference draws on the CPU and copies 64 KB per draw over PCIe; pre-drawn noise can be injected (``z=``);
-* votes are counted on the device into int64 counters (certified_robust.py:58-67) and read back once;
-* with ``world_size > 1`` each rank takes a contiguous slice of the draw indices and only the vote counts
-  are all-reduced (NCCL via the C ABI, or any ``allreduce`` callable -- gloo in the CPU tests).  Because the
-  noise is keyed on the draw index, the draws -- and therefore the summed integer counts -- do not depend
-  on the number of ranks.
+* a ``certify`` call turns ALL its clips and both of its passes (n_0 selection draws, n estimation draws,
+  certified_robust.py:81-93) into one clip-major work list of (clip, draw) items and runs it in full batches that
+  may span clips -- the reference (and r01 of this package) ran clip by clip, pass by pass, which at 8 GPUs left
+  12-draw slivers of a 64-batch for the n_0 = 100 pass;
+* votes are counted on the device into int64 counters per (pass, clip) (certified_robust.py:58-67) and read back
+  once per call; the Clopper-Pearson bound and the radius stay on the host in float64 like the reference;
+* with ``world_size > 1`` each rank takes a contiguous slice of the work list and only the vote counts are
+  all-reduced, once per call (NCCL via the C ABI, or any ``allreduce`` callable -- gloo in the CPU tests).  Because
+  the noise is keyed on (clip, draw), the draws -- and therefore the summed integer counts -- do not depend on the
+  number of ranks or on the batch size.
 """
 
 import ctypes
@@ -95,8 +100,10 @@ class RobustCertificate():
     ``world_size > 1`` every rank must be built with the same seed and make the same sequence of calls."""
 
     def __init__(self, classifier: torch.nn.Module, transform=None, denoiser=None, one_shot_rev: bool = False,
-                 num_classes=10, seed: int = None, rank: int = 0, world_size: int = 1, allreduce=None):
+                 num_classes=10, seed: int = None, rank: int = 0, world_size: int = 1, allreduce=None,
+                 pad_batches: bool = True):
         self.classifier = classifier
+        self.pad_batches = pad_batches
         self.transform = transform
         self.denoiser = denoiser
         self.num_classes = num_classes
@@ -151,15 +158,20 @@ class RobustCertificate():
             z = z.to(device=x.device, dtype=torch.float32).contiguous()
             assert z.numel() == C * per_clip * L, "injected noise must be (clips, draws, 1, L)"
         if self._x_in is None or self._x_in.shape != (batch_size, 1, L) or self._x_in.device != x.device:
-            self._x_in = torch.empty(batch_size, 1, L, dtype=torch.float32, device=x.device)
+            self._x_in = torch.zeros(batch_size, 1, L, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             for s, b in work_batches(C, per_clip, self.rank, self.world_size, batch_size):
-                x_in = self._x_in[:b]
+                # A ragged last batch still goes through the denoiser / transform / classifier as a FULL batch (its
+                # tail rows hold the previous batch's inputs and their votes are not counted): every launch has one
+                # shape, so tensor maps, cuDNN plans and autotuning are reused, and -- because the consumer's cuDNN
+                # kernels are only reproducible per batch shape -- a draw's vote does not depend on how many ranks
+                # or what batch boundaries the work list was cut into.
+                x_in = self._x_in if self.pad_batches else self._x_in[:b]
                 _lib.check(lib.ap_smooth_inputs_batch(x.data_ptr(), L, b, s, per_clip, first_draw, float(sigma),
                                                       float(scale), z.data_ptr() if z is not None else None,
                                                       self.seed, clip_key0, x_in.data_ptr(), _lib.stream_ptr()))
                 logits = self.forward(x_in).to(torch.float32).contiguous()
-                assert logits.shape == (b, K)
+                assert logits.shape == (x_in.shape[0], K)
                 _lib.check(lib.ap_vote_counts_batch(logits.data_ptr(), b, K, s, per_clip, n_split, C,
                                                     counts.data_ptr(), _lib.stream_ptr()))
             if self.allreduce is not None:

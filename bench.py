@@ -242,6 +242,11 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
             self.spans.append((e0, e1))
             return out
 
+    # cuDNN autotuning picks its convolution algorithms by timing, so two processes can choose differently and the bf16
+    # consumer's logits then differ in the last bits -- enough to flip a near-tie draw's vote.  With autotuning off
+    # (and RobustCertificate's fixed batch shape) every rank of every N runs the same kernels and the vote counts
+    # are identical at every N: `counts_checksum`.
+    torch.backends.cudnn.benchmark = False
     allreduce = TimedAllReduce(rank, world)  # a 1-rank communicator at N = 1: the same call path at every N
     n0, n, clips, sigma, bs = args.certify_n0, args.certify_n, args.certify_clips, 0.25, 64
     dw = ap.DiffWave(model, hp, reverse_timestep=34, seed=0)
@@ -291,6 +296,7 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
         "draws_per_s": total / (ms * 1e-3), "seconds_per_clip": ms * 1e-3 / clips, "ms": ms, "n": n, "n0": n0,
         "clips": clips, "n_gpus": world, "scaling": "strong",
         "y_pred": y_pred.tolist(), "radius": [round(float(r), 4) for r in radius.tolist()],
+        "cudnn_benchmark": False,
         "counts_checksum": int((counts * torch.arange(1, 11)).sum() + 31 * (counts_0 * torch.arange(1, 11)).sum()),
     }
     collective = {"name": "ncclAllReduce int64 sum (ap_allreduce_counts, NCCL via dlopen)", "calls": calls,

@@ -34,7 +34,7 @@ def main():
     args = p.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = False  # same consumer kernels in every process: identical vote counts at every N
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     allreduce = NcclCountsAllReduce(rank, world)

@@ -2,7 +2,7 @@
 
 Two roots: ``/root/reference`` (the build container; used by ``oracle/make_golden.py`` to generate the committed
 fixtures) and ``oracle/_ref`` (the hot-path files staged by ``oracle/stage_ref.py``, which travel to the GPU box;
-used by ``bench.py --impl reference`` and ``tools/gpu_eager_reference.py``).  Nothing under ``tests -m gpu`` or
+used by ``bench.py --impl reference`` and ``tests/gpu_eager_reference.py``).  Nothing under ``tests -m gpu`` or
 ``smoke()`` calls this.
 
 Recipe: put the checkout on ``sys.path``, stub the

@@ -1,8 +1,8 @@
 """The reference's own modules (oracle/_ref: unmodified files staged by oracle/stage_ref.py) run as PyTorch eager on
 the B200, BASELINE configs[1] shape (B = 64, DDPM t*=2 -> torchaudio log-mel -> ResNeXt-29): the "bar to beat" of
-SURVEY.md section 2.1, recorded beside the CPU number.  A tools script, not part of bench.py's timed region.
+SURVEY.md section 2.1, recorded beside the CPU number.  A measurement script kept under tests/ (it executes oracle/_ref through the oracle harness, which only tests/, smoke() and bench.py's CPU leg may do), not part of bench.py's timed region.
 
-    python tools/gpu_eager_reference.py [--batch 64] [--steps 5] > profiles/r02_gpu_eager_reference.json
+    python tests/gpu_eager_reference.py [--batch 64] [--steps 5] > profiles/r02_gpu_eager_reference.json
 
 Prints one JSON object with clips/s for fp32 (TF32 off), TF32-allowed convolutions, and this package on the same
 box and inputs, plus the agreement of the reference-on-GPU predictions with ours (same injected noise)."""

@@ -41,3 +41,17 @@ def test_fused_inference_form_is_exact_in_fp32():
         a, b = clf(x), fused(x)
     assert float((a - b).norm() / a.norm()) < 1e-5
     assert sum(1 for m in fused.modules() if isinstance(m, torch.nn.BatchNorm2d)) == 0
+
+
+def test_fused_form_is_inference_only():
+    """FusedResNeXt has no backward; an input that requires grad must fail loudly, not lose its gradient."""
+    import pytest
+
+    clf = ap.CifarResNeXt(nlabels=10, in_channels=1)
+    clf.load_state_dict(o_resnext.make_state_dict(4321))
+    fused = ap.FusedResNeXt(clf.eval(), dtype=torch.float32)
+    x = torch.zeros(1, 1, 32, 32, requires_grad=True)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        fused(x)
+    with torch.no_grad():
+        assert fused(x).shape == (1, 10)

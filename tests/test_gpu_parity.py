@@ -430,6 +430,20 @@ def test_logmel_ragged_lengths_and_silence():
     assert float(z.max()) == -100.0 and float(z.min()) == -100.0  # clamp at 1e-10 -> -100 dB
 
 
+def test_logmel_large_batch_equals_per_clip_runs():
+    """130 clips = 2080 frame pairs > the 1036 resident CTAs: the persistent loop of the log-mel kernel re-uses its
+    shared-memory buffers for several items; every clip must equal its own single-clip launch bit for bit, and the
+    oracle within the dB gate."""
+    from oracle import mel as o_mel
+
+    tr = ap.LogMelSpectrogram().cuda()
+    x = W.make_clips(130, 16000, seed=77).cuda()
+    big = tr(x)
+    for i in (0, 1, 64, 65, 129):
+        assert torch.equal(big[i:i + 1], tr(x[i:i + 1])), i
+    assert float((big[100:104].cpu() - o_mel.log_mel(x[100:104].cpu())).abs().max()) < 2e-2
+
+
 def test_logmel_backward_vs_autograd_of_oracle():
     from oracle import mel as o_mel
 

@@ -72,10 +72,15 @@ class NcclCountsAllReduce:
         _lib.check(self.lib.ap_allreduce_counts(self.comm, counts.data_ptr(), counts.numel(), _lib.stream_ptr()))
         return counts
 
+    def close(self):
+        """Destroy the communicator now (otherwise at garbage collection)."""
+        if getattr(self, "comm", None):
+            self.lib.ap_comm_destroy(self.comm)
+            self.comm = None
+
     def __del__(self):
         try:
-            if getattr(self, "comm", None):
-                self.lib.ap_comm_destroy(self.comm)
+            self.close()
         except Exception:
             pass
 

@@ -288,6 +288,8 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
         allreduce(probe)
     torch.cuda.synchronize()
     in_step_ms = sum(a.elapsed_time(b) for a, b in allreduce.spans) / 10
+    allreduce.spans = []
+    allreduce.close()  # before the JSON line is printed: nothing NCCL logs at teardown may follow it on stdout
     counts_0, counts = RC.last_counts
     certify = {
         "workload": "BASELINE configs[3]: %d clips x (n_0 = %d + n = %d) smoothing draws, sigma = %.2f (t* = 34): "
@@ -513,9 +515,11 @@ def run_ours(args):
         traffic_file = os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")
         if os.path.exists(traffic_file) and args.precision == "bf16":  # the ncu capture is of the bf16 kernel
             line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
-        print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)  # the last thing on stdout
 
 
 def main():

@@ -167,10 +167,23 @@ struct Mode : Tc {
 #ifndef AP_LAYER_STAGES
 #define AP_LAYER_STAGES 5
 #endif
-  static constexpr int kLayerStages = kTf32 ? 3 : AP_LAYER_STAGES;
+  // tf32 layer kernel: the operand tile holds HALF of the 256 channels at a time (kSplit): the gate of chunk 0 is
+  // consumed by the first half of GEMM2 before chunk 1's gate overwrites it, and the residual input is re-loaded and
+  // turned into h_next in two halves.  That frees 64 KB: 5 ring stages instead of 3 (the ring is latency-sensitive).
+  static constexpr bool kSplit = kTf32;
+#ifdef AP_TF32_NO_SPLIT  // A/B variant: the r01 layout (full 128 KB operand tile, 3 stages)
+#undef AP_TF32_NO_SPLIT
+#define AP_TF32_NO_SPLIT 1
+#else
+#define AP_TF32_NO_SPLIT 0
+#endif
+  static constexpr bool kSplitTile = kSplit && !AP_TF32_NO_SPLIT;
+  static constexpr int kTileSubs = kSplitTile ? kSubs / 2 : kSubs;   // sub-tiles resident in the layer kernel's operand tile
+  static constexpr uint32_t kLayerTileBytes = kTileSubs * kABytes;
+  static constexpr int kLayerStages = kTf32 ? (kSplitTile ? 5 : 3) : AP_LAYER_STAGES;
   // tail: 4 -> 5 stages (possible since the bias tables moved to the constant bank): 4.48 -> 3.68 ms per launch
   static constexpr int kTailStages = kTf32 ? 3 : 5;
-  static constexpr uint32_t kLayerSmem = kLayerStages * kStageBytes + kTileBytes + 32 * 8 + 1024;
+  static constexpr uint32_t kLayerSmem = kLayerStages * kStageBytes + kLayerTileBytes + 32 * 8 + 1024;
   static constexpr uint32_t kTailSmem = kTailStages * kStageBytes + kTileBytes + 2 * 128 * 4 + 32 * 8 + 1024;
   static_assert(kLayerStages <= 6 && kTailStages <= 6, "barrier slots");
   static_assert(kLayerSmem <= 232448 && kTailSmem <= 232448, "over the 227 KB per-CTA shared-memory limit");
@@ -323,7 +336,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   constexpr int kStages = T::kLayerStages;
   constexpr int kSubs = T::kSubs, kSubK = T::kSubK;
   uint8_t* gate_s = smem + kStages * T::kStageBytes;  // the operand tile: gate, then x, then h_next
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gate_s + T::kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gate_s + T::kLayerTileBytes);
   uint64_t* full = bars;             // [kStages] TMA -> MMA            (leader's copy is the live one)
   uint64_t* empty = bars + 6;        // [kStages] MMA -> TMA            (per CTA, multicast commit)
   uint64_t* d1_full = bars + 12;     // [2] chunk accumulator ready     MMA -> epilogue (per CTA)
@@ -332,7 +345,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
   uint64_t* d2_empty = bars + 17;    //     residual accumulator drained epilogue -> MMA (leader)
   uint64_t* tile_free = bars + 18;   //     gate tile dead (GEMM2 + gate stores done)  epilogue -> x producer
   uint64_t* x_full = bars + 19;      // [kSubs <= 8] x sub-tile k landed in the operand tile    x producer -> epilogue
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* g2a_done = bars + 27;    //     split tile: first half of GEMM2 has read the gate of chunk 0   MMA -> epilogue (per CTA)
+  uint64_t* half_free = bars + 28;   //     split tile: first half of h_next stored, tile reusable          epilogue -> x producer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 29);
+  constexpr bool kSplitTile = T::kSplitTile;
+  constexpr int kTileSubs = T::kTileSubs;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -352,6 +369,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, 2 * T::kEpiWarps);
     mbar_init(tile_free, T::kEpiWarps);
+    mbar_init(g2a_done, 1);
+    mbar_init(half_free, T::kEpiWarps);
     fence_mbar_init();
     tma_prefetch_desc(&tm_h);
     tma_prefetch_desc(&tm_w1);
@@ -453,11 +472,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
           mbar_wait(&full[s], (it / kStages) & 1, 6);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = gdesc0 + static_cast<uint64_t>((ks * kABytes) >> 4);
+            const int asub = kSplitTile ? (ks & (kTileSubs - 1)) : ks;  // split tile: both gate halves live in sub-tiles 0..3
+            const uint64_t da = gdesc0 + static_cast<uint64_t>((asub * kABytes) >> 4);
             const uint64_t db = desc0 + static_cast<uint64_t>((s * T::kStageBytes + kABytes) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_pair<kTf32>(bufA, da + 2 * k, db + 2 * k, T::kIdesc, (ks | k) != 0);
             umma_commit_pair(&empty[s]);
+            if (kSplitTile && ks == kSubs / 2 - 1) umma_commit_pair(g2a_done);  // chunk 0's gate may be overwritten
             if (ks == kSubs - 1) umma_commit_pair(d2_full);
           }
           __syncwarp();
@@ -474,12 +495,23 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       mbar_wait(tile_free, i & 1, 9);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kSubs; ++k) {
+        for (int k = 0; k < kTileSubs; ++k) {
           mbar_arrive_expect_tx(&x_full[k], kABytes);
           tma_load_3d(gate_s + k * kABytes, &tm_h, &x_full[k], k * kSubK, tc.l0, tc.b);
         }
       }
       __syncwarp();
+      if constexpr (kSplitTile) {  // second half of the channels, once the first half of h_next has left the tile
+        mbar_wait(half_free, i & 1, 24);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTileSubs; ++k) {
+            mbar_arrive_expect_tx(&x_full[k], kABytes);
+            tma_load_3d(gate_s + k * kABytes, &tm_h, &x_full[k], (kTileSubs + k) * kSubK, tc.l0, tc.b);
+          }
+        }
+        __syncwarp();
+      }
     }
   } else if (warp >= kEpiWarp0) {
     // ======================= epilogue (8 warps, each owns rows [32q,+32) of 64-channel chunks {hh, 2+hh}) ====
@@ -505,6 +537,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       for (int c = 0; c < 2; ++c) {
         mbar_wait(&d1_full[c], p, 7);
         tc_fence_after();
+        if (kSplitTile && c == 1) {
+          // chunk 1's gate goes where chunk 0's is: the first half of GEMM2 and this warp's gate stores must have read it
+          mbar_wait(g2a_done, p, 23);
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
         const uint32_t buf = (c ? bufB : bufA) + lane_addr;
 #pragma unroll
         for (int itn = 0; itn < 2; ++itn) {
@@ -524,7 +562,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
             for (int j = 0; j < 32; ++j)
               o[j] = gate_act<kTf32>(__uint_as_float(rt[j]) + bt[j], __uint_as_float(rs[j]) + bs[j]);
           }
-          tile_store32<kTf32>(gate_s, row, 4 * c + 2 * hh + itn, o, a.round_bias);
+          const int gg = 4 * c + 2 * hh + itn;  // 32-channel group of the gate
+          tile_store32<kTf32>(gate_s, row, kSplitTile ? (gg & (kTileSubs - 1)) : gg, o, a.round_bias);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -536,7 +575,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
 #pragma unroll
             for (int s = 0; s < T::kSubsPer64; ++s) {
               const int sub = (2 * c + hh) * T::kSubsPer64 + s;
-              tma_store_4d(&tm_gate_st, gate_s + sub * kABytes + q * 32 * 128, sub * kSubK, l0 + q * 32, b, a.layer);
+              const int ssub = kSplitTile ? (sub & (kTileSubs - 1)) : sub;
+              tma_store_4d(&tm_gate_st, gate_s + ssub * kABytes + q * 32 * 128, sub * kSubK, l0 + q * 32, b, a.layer);
             }
             tma_store_commit();
           }
@@ -560,33 +600,57 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int g = 2 * k + half;  // 32-channel group
-          if (half == 0 || kTf32) mbar_wait(&x_full[g * 32 / kSubK], p, 10);
+          // split tile: channels 0-127 (kk = 0) and 128-255 (kk = 1) pass through sub-tiles 0..3 one after the other;
+          // x_full[s] then completes twice per tile, phases 2i and 2i + 1
+          const int gs = kSplitTile ? (g & (kTileSubs - 1)) : g;
+          if (half == 0 || kTf32) mbar_wait(&x_full[kSplitTile ? gs : g * 32 / kSubK], kSplitTile ? (kk & 1) : p, 10);
           if (half == 0) tmem_ld_wait();
           const uint32_t* r = half ? r1 : r0;
           const float* cc = bias.c2 + g * 32;
           float v[32];
-          tile_load32<kTf32>(gate_s, row, g, v, a.round_bias);
+          tile_load32<kTf32>(gate_s, row, gs, v, a.round_bias);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], kSqrtHalf, __uint_as_float(r[j]) + cc[j]);
-          tile_store32<kTf32>(gate_s, row, g, v, a.round_bias);
+          tile_store32<kTf32>(gate_s, row, gs, v, a.round_bias);
         }
         if (kk == 1) {  // all of this warp's accumulator columns are in registers / consumed
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(d2_empty_l);
         }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && a.write_h && !AP_ABL(a, 4)) {
+        if constexpr (kSplitTile) {  // this half of h_next leaves now; after kk = 0 the tile is handed back for x's second half
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (a.write_h && !AP_ABL(a, 4)) {
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-          for (int s = 0; s < T::kSubsPer64; ++s) {
-            const int sub = (hh + 2 * kk) * T::kSubsPer64 + s;
-            tma_store_3d(&tm_h_st, gate_s + sub * kABytes + q * 32 * 128, sub * kSubK, l0 + q * 32, b);
+              for (int s = 0; s < T::kSubsPer64; ++s) {
+                const int sub = k * T::kSubsPer64 + s;
+                tma_store_3d(&tm_h_st, gate_s + (sub & (kTileSubs - 1)) * kABytes + q * 32 * 128, sub * kSubK, l0 + q * 32, b);
+              }
+              tma_store_commit();
+            }
+            if (kk == 0) {
+              tma_store_wait_read();
+              mbar_arrive(half_free);
+            }
           }
-        tma_store_commit();
+          __syncwarp();
+        }
+      }
+      if constexpr (!kSplitTile) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && a.write_h && !AP_ABL(a, 4)) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int s = 0; s < T::kSubsPer64; ++s) {
+              const int sub = (hh + 2 * kk) * T::kSubsPer64 + s;
+              tma_store_3d(&tm_h_st, gate_s + sub * kABytes + q * 32 * 128, sub * kSubK, l0 + q * 32, b);
+            }
+          tma_store_commit();
+        }
       }
     }
     if (lane == 0) tma_store_wait_all();

@@ -231,7 +231,10 @@ def fx_frontend(c):
     # ---- A14: torchaudio log-mel; A18: ResNeXt-29 8x64 (consumer, calibrated synthetic checkpoint);
     # A15: AcousticSystem composition (defender -> transform -> classifier) --
     x2 = W.make_waveforms(2, 16000, seed=0)
-    y_t2 = torch.from_numpy(np.load(os.path.join(OUT, "ddpm_t2.npz"))["purified"])
+    src = os.path.join(OUT, "ddpm_t2.npz")  # written by the `ddpm` step; fall back to the committed fixture
+    if not os.path.exists(src):
+        src = os.path.join(ROOT, "tests", "golden", "ddpm_t2.npz")
+    y_t2 = torch.from_numpy(np.load(src)["purified"])
     xm = torch.cat([x2, y_t2, W.make_clips(4, 16000, seed=20)], dim=0)
     with torch.no_grad():
         spec = c.transform(xm)

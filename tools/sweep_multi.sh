@@ -1,4 +1,4 @@
-# usage: bash tools/_run_multi.sh N   (under gpurun --gpus N)
+# usage: bash tools/sweep_multi.sh N   (under gpurun --gpus N)
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 $TR --master-port 29530 tools/sweep.py --batches 64,256,1024 --tstars 1,2,3,5,10 --json gpurun_out/r02_sweep_${N}gpu.jsonl 2>&1 | grep -v -i "warn\|OMP_NUM\|\*\*\*\*" | tee gpurun_out/r02_sweep_ddpm_${N}gpu.md | tail -4

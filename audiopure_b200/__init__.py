@@ -8,6 +8,7 @@ Drop-in counterparts of the reference's modules for that path (same names and ca
     acoustic_system.AcousticSystem                     acoustic_system.py
     transforms.LogMelSpectrogram                       torchaudio MelSpectrogram + AmplitudeToDB (eval scripts)
     certified_robust.RobustCertificate                 robustness_eval/certified_robust.py
+    blackbox.EOT / blackbox.NES                        robustness_eval/_EOT.py, robustness_eval/_NES.py
     classifier.CifarResNeXt                            audio_models/ConvNets_SpeechCommands/models/resnext.py (consumer)
 
 All compute on the path runs in hand-written CUDA kernels behind the C ABI of include/audiopure_b200.h
@@ -15,6 +16,7 @@ All compute on the path runs in hand-written CUDA kernels behind the C ABI of in
 """
 
 from .acoustic_system import AcousticSystem  # noqa: F401
+from .blackbox import EOT, NES  # noqa: F401
 from .certified_robust import RobustCertificate  # noqa: F401
 from .classifier import CifarResNeXt, FusedResNeXt  # noqa: F401
 from .diffwave_ddpm import DiffWave, create_diffwave_model  # noqa: F401

@@ -223,7 +223,6 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
     import torch
     import torch.distributed as dist
 
-    from audiopure_b200 import _lib
     from audiopure_b200.certified_robust import NcclCountsAllReduce
 
     class TimedAllReduce(NcclCountsAllReduce):

@@ -7,7 +7,6 @@ tensor-core kernels are tcgen05 / TMEM / TMA native and that no legacy mma.sync 
 import os
 import re
 import subprocess
-import sys
 from collections import Counter, OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,7 +1,6 @@
 """Launches the HBM-bound kernels of the path once each at bench size (64 clips) and at 1024 clips, for ncu
 (tools/ncu_run.sh), and prints their CUDA-event times (mean of 20 back-to-back launches after warm-up)."""
 
-import ctypes
 import os
 import sys
 

@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--t-star", type=int, default=T_STAR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clips", type=int, default=4, help="clips per CPU step (BASELINE configs[0]: batch 4)")
+    ap.add_argument("--max-chunk", type=int, default=None,
+                    help="clips per pass through the 36 layers (default: the package's; smaller keeps the residual stream in L2)")
     ap.add_argument("--no-certify", action="store_true", help="skip the certification leg")
     ap.add_argument("--certify-clips", type=int, default=4)
     ap.add_argument("--certify-n", type=int, default=10000)
@@ -341,7 +343,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    model = ap.WaveNet_Speech_Commands(**S.DEFAULT_WAVENET_CONFIG, precision=args.precision)
+    model = ap.WaveNet_Speech_Commands(**S.DEFAULT_WAVENET_CONFIG, precision=args.precision, max_chunk=args.max_chunk)
     model.load_state_dict(S.diffwave_state_dict(1234))
     model = model.to(dev).eval()
     hp = ap.calc_diffusion_hyperparams(**S.DEFAULT_DIFFUSION_CONFIG)

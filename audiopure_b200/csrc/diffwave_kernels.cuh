@@ -14,6 +14,8 @@
 // K = input channels (x taps).  A = activations, B = weights, both K-major, 128-byte swizzle.
 #pragma once
 
+#include <type_traits>
+
 #include "sm100.cuh"
 
 namespace ap {
@@ -515,9 +517,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     }
   } else if (warp >= kEpiWarp0) {
     // ======================= epilogue (8 warps, each owns rows [32q,+32) of 64-channel chunks {hh, 2+hh}) ====
-    const int e = warp - kEpiWarp0;
+    // The body is instantiated once per warpgroup (hh = 0 / 1) with the chunk and half loops unrolled, so that every
+    // bias index is a compile-time constant and the adds read the constant bank directly instead of through LDC.
     const int q = warp & 3;   // TMEM lane quarter this warp may read
-    const int hh = e >> 2;    // warpgroup: which 64-channel chunks / which half of a gate chunk
+    auto epilogue = [&](auto hh_c) {
+    constexpr int hh = decltype(hh_c)::value;  // warpgroup: which 64-channel chunks / which half of a gate chunk
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t gate_ready0 = mapa_u32(&gate_ready[0], 0);
@@ -534,6 +538,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       __syncwarp();
 
       // ---- gate: two chunks of 128 gate channels; this warp does channels [64hh, 64hh+64) of each ----
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
         mbar_wait(&d1_full[c], p, 7);
         tc_fence_after();
@@ -591,7 +596,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         mbar_arrive(tile_free);
       }
       __syncwarp();
-#pragma unroll 1
+#pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         const int k = hh + 2 * kk;  // 64-channel chunk
         uint32_t r0[32], r1[32];
@@ -653,6 +658,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         }
       }
     }
+    };
+    if (((warp - kEpiWarp0) >> 2) == 0)
+      epilogue(std::integral_constant<int, 0>{});
+    else
+      epilogue(std::integral_constant<int, 1>{});
     if (lane == 0) tma_store_wait_all();
   }
 

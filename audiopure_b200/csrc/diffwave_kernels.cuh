@@ -6,7 +6,7 @@
 //            128-step tile is one TMA box at row offset l0 + (tap-1)*dilation; the 3-D tensor map (c, l, b)
 //            zero-fills rows outside [0, L), which IS the conv's zero padding and keeps taps from bleeding
 //            across clips.  h_n already contains the "+ fc_t(emb)" shift of layer n (WaveNet.py:82-84).
-//   gate   : [layers][B][L][256] bf16 -- tanh*sigmoid output of every layer, kept so that the 36 skip
+//   gate   : [layers][B][L][256] bf16 -- 2 * tanh*sigmoid output of every layer, kept so that the 36 skip
 //            projections become ONE K = layers*256 GEMM in the tail kernel (fp32 accumulation in TMEM)
 //            instead of a 16 MB/clip fp32 read-modify-write per layer.
 //
@@ -195,43 +195,52 @@ struct Mode : Tc {
 // tf32: `round_bias` (0x1000 when the tensor core truncates the low 13 mantissa bits, see ap_create) is added to
 // the fp32 bit pattern on the way in, so that truncation rounds to nearest, and taken off again on the way out,
 // so the residual stream itself stays exact fp32.
+// Shared-memory accesses of the epilogues go through 32-bit shared-window addresses (st.shared / ld.shared): the
+// generic-pointer form costs 64-bit address arithmetic per access.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 template <bool kTf32>
-__device__ __forceinline__ void tile_store32(uint8_t* tile, int row, int g, const float (&v)[32], uint32_t round_bias) {
+__device__ __forceinline__ void tile_store32(uint32_t tile, int row, int g, const float (&v)[32], uint32_t round_bias) {
   if constexpr (kTf32) {
-    uint8_t* sub = tile + g * kABytes;
+    const uint32_t sub = tile + g * kABytes;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<uint4*>(sub + sw128_offset(row, c)) =
-          make_uint4(__float_as_uint(v[4 * c]) + round_bias, __float_as_uint(v[4 * c + 1]) + round_bias,
-                     __float_as_uint(v[4 * c + 2]) + round_bias, __float_as_uint(v[4 * c + 3]) + round_bias);
+      sts128(sub + sw128_offset(row, c), __float_as_uint(v[4 * c]) + round_bias, __float_as_uint(v[4 * c + 1]) + round_bias,
+             __float_as_uint(v[4 * c + 2]) + round_bias, __float_as_uint(v[4 * c + 3]) + round_bias);
   } else {
-    uint8_t* sub = tile + (g >> 1) * kABytes;
+    const uint32_t sub = tile + (g >> 1) * kABytes;
     const int q0 = (g & 1) * 4;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<uint4*>(sub + sw128_offset(row, q0 + c)) =
-          make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                     pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+      sts128(sub + sw128_offset(row, q0 + c), pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+             pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
   }
 }
 template <bool kTf32>
-__device__ __forceinline__ void tile_load32(const uint8_t* tile, int row, int g, float (&v)[32], uint32_t round_bias) {
+__device__ __forceinline__ void tile_load32(uint32_t tile, int row, int g, float (&v)[32], uint32_t round_bias) {
   if constexpr (kTf32) {
-    const uint8_t* sub = tile + g * kABytes;
+    const uint32_t sub = tile + g * kABytes;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(sub + sw128_offset(row, c));
+      const uint4 u = lds128(sub + sw128_offset(row, c));
       v[4 * c] = __uint_as_float(u.x - round_bias);
       v[4 * c + 1] = __uint_as_float(u.y - round_bias);
       v[4 * c + 2] = __uint_as_float(u.z - round_bias);
       v[4 * c + 3] = __uint_as_float(u.w - round_bias);
     }
   } else {
-    const uint8_t* sub = tile + (g >> 1) * kABytes;
+    const uint32_t sub = tile + (g >> 1) * kABytes;
     const int q0 = (g & 1) * 4;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(sub + sw128_offset(row, q0 + c));
+      const uint4 u = lds128(sub + sw128_offset(row, q0 + c));
       v[8 * c] = bf16_lo(u.x);
       v[8 * c + 1] = bf16_hi(u.x);
       v[8 * c + 2] = bf16_lo(u.y);
@@ -287,10 +296,11 @@ __device__ __forceinline__ uint32_t live_tap_mask(int unit, int num_tiles, int t
 //   GEMM1  D1[128 x 512] = sum_{tap,c} h[l + (tap-1)d][c] * W1[o][c][tap]     (K = 768)
 //          issued as two N = 256 chunks; chunk c holds gate channels [128c, 128c+128): TMEM columns
 //          [0,128) are their tanh rows, [128,256) their sigmoid rows (W1 rows are permuted at pack time).
-//   gate   g = tanh(D1t + b) * sigmoid(2 (D1s + b))   (sigmoid rows are packed pre-halved, see gate_act)
+//   gate   g2 = 2 tanh(D1t + b) * sigmoid(2 (D1s + b))   (sigmoid rows packed pre-halved; TWICE the gate is kept, its 1/2
+//          is folded into the res / skip weights: see gate_act)
 //          -> bf16 -> shared memory (K-major, SW128) AND, by TMA
 //          store from that same shared tile, to gate[layer] in HBM for the tail's skip GEMM.
-//   GEMM2  D2[128 x 256] = g * (sqrt(.5) W_res)^T                                  (K = 256)
+//   GEMM2  D2[128 x 256] = g2 * (1/2 sqrt(.5) W_res)^T                             (K = 256)
 //   out    h_next = sqrt(.5) * h + D2 + (sqrt(.5) b_res + part_{n+1})   (the residual term is the shifted
 //          input -- SURVEY section 0 fact 1 -- and the next layer's shift is folded in here).
 //
@@ -526,6 +536,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t gate_ready0 = mapa_u32(&gate_ready[0], 0);
     const uint32_t d2_empty_l = mapa_u32(d2_empty, 0);
+    const uint32_t gate_sa = smem_u32(gate_s);
     int i = 0;
     for (int u = unit0; 2 * u < a.num_tiles; u += units, ++i) {
       const uint32_t p = i & 1;
@@ -568,7 +579,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
               o[j] = gate_act<kTf32>(__uint_as_float(rt[j]) + bt[j], __uint_as_float(rs[j]) + bs[j]);
           }
           const int gg = 4 * c + 2 * hh + itn;  // 32-channel group of the gate
-          tile_store32<kTf32>(gate_s, row, kSplitTile ? (gg & (kTileSubs - 1)) : gg, o, a.round_bias);
+          tile_store32<kTf32>(gate_sa, row, kSplitTile ? (gg & (kTileSubs - 1)) : gg, o, a.round_bias);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -613,10 +624,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
           const uint32_t* r = half ? r1 : r0;
           const float* cc = bias.c2 + g * 32;
           float v[32];
-          tile_load32<kTf32>(gate_s, row, gs, v, a.round_bias);
+          tile_load32<kTf32>(gate_sa, row, gs, v, a.round_bias);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], kSqrtHalf, __uint_as_float(r[j]) + cc[j]);
-          tile_store32<kTf32>(gate_s, row, gs, v, a.round_bias);
+          tile_store32<kTf32>(gate_sa, row, gs, v, a.round_bias);
         }
         if (kk == 1) {  // all of this warp's accumulator columns are in registers / consumed
           tc_fence_before();
@@ -677,7 +688,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------------
 // K2: skip GEMM + output head + reverse-step update, persistent over pairs of 128-step tiles.
 //
-//   GEMMs  S[128 x 256]  = sum_n gate_n * (sqrt(1/N) W_skip,n)^T      (K = N*256; WaveNet.py:95,133,135)
+//   GEMMs  S[128 x 256]  = sum_n (2 gate_n) * (1/2 sqrt(1/N) W_skip,n)^T   (K = N*256; WaveNet.py:95,133,135)
 //   head   y  = relu(bf16(S + bias) * W_f^T + b_f)                     (GEMM, K = 256; WaveNet.py:160-161)
 //          eps = y . w_o + b_o                                          (256 -> 1 dot; WaveNet.py:162)
 //   update x_out = ca * x_in + cb * eps + cc * z                        (diffwave_ddpm.py:159,99-102 /
@@ -872,7 +883,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tm_gate, const __grid_constant__
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias.bs[j0 + j];
-        tile_store32<kTf32>(s_tile, row, j0 >> 5, v, a.round_bias);
+        tile_store32<kTf32>(smem_u32(s_tile), row, j0 >> 5, v, a.round_bias);
       }
       tc_fence_before();
       fence_proxy_async_smem();

@@ -331,24 +331,38 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// The sigmoid rows of the packed dilated-conv weights and bias carry a factor 1/2 (exact in bf16 / tf32, folded in
-// at pack time), so the GEMM delivers s_half = s / 2 and sigmoid(s) = 1/2 tanh(s_half) + 1/2 costs one MUFU + one FMA.
-#ifdef AP_AB_NO_FOLD  // timing-only A/B variant (profiles/r02_ablation.md): the round-1 epilogue's extra multiply
-__device__ __forceinline__ float sigmoid_fast_half(float s_half) { return fmaf(0.5f, tanh_fast(0.5f * s_half), 0.5f); }
+// Gate arithmetic.  Two exact power-of-two foldings at pack time keep the epilogue short:
+//  * the sigmoid rows of the packed dilated-conv weights and bias carry a factor 1/2, so the GEMM delivers
+//    s_half = s / 2 and sigmoid(s) = 1/2 tanh(s_half) + 1/2 needs no multiply on the way in;
+//  * the kernels produce and store TWICE the gate, 2 tanh(t) sigmoid(s) = tanh(t) (tanh(s_half) + 1) -- one FMA after
+//    the two MUFU ops -- and the factor 1/2 lives in the packed res / skip weights that consume it.
+// Scaling by 2 commutes with rounding to bf16 / tf32, so the results are bit-identical to the unfolded form.
+#ifdef AP_AB_NO_FOLD  // timing-only A/B variant (profiles/r02_ablation.md): the round-1 epilogue's extra multiplies
+__device__ __forceinline__ float gate2_fast(float t, float s_half) {
+  return 2.0f * (tanh_fast(t) * fmaf(0.5f, tanh_fast(0.5f * s_half), 0.5f));
+}
+#elif defined(AP_AB_GATE_FMUL)  // timing-only: the FFMA + FMUL form used before the factor 2 was folded (values off by 1/2)
+__device__ __forceinline__ float gate2_fast(float t, float s_half) {
+  return tanh_fast(t) * fmaf(0.5f, tanh_fast(s_half), 0.5f);
+}
 #else
-__device__ __forceinline__ float sigmoid_fast_half(float s_half) { return fmaf(0.5f, tanh_fast(s_half), 0.5f); }
+__device__ __forceinline__ float gate2_fast(float t, float s_half) {
+  const float tt = tanh_fast(t);
+  return fmaf(tt, tanh_fast(s_half), tt);
+}
 #endif
 // TF32 mode: tanh.approx (2^-11 relative) would be the largest error left, so use fp32-accurate forms there:
-// 1 / (1 + exp(-2 s_half)), the factor 2 folded into the exp2 scaling.
-__device__ __forceinline__ float sigmoid_acc_half(float s_half) {
-  return __fdividef(1.0f, 1.0f + exp2f(-2.8853900817779268f * s_half));
+// 2 sigmoid(s) = 2 / (1 + exp(-2 s_half)), the factor 2 of the exponent folded into the exp2 scaling.
+__device__ __forceinline__ float gate2_acc(float t, float s_half) {
+  return tanhf(t) * __fdividef(2.0f, 1.0f + exp2f(-2.8853900817779268f * s_half));
 }
+// -> 2 * tanh(t) * sigmoid(2 * s_half)
 template <bool kAccurate>
 __device__ __forceinline__ float gate_act(float t, float s_half) {
   if constexpr (kAccurate)
-    return tanhf(t) * sigmoid_acc_half(s_half);
+    return gate2_acc(t, s_half);
   else
-    return tanh_fast(t) * sigmoid_fast_half(s_half);
+    return gate2_fast(t, s_half);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -167,10 +167,10 @@ class WaveNet_Speech_Commands(nn.Module):
             w1[n] = w[perm] * half
             b1[n] = b.to(dev)[perm] * half[:, 0]
             wr, br = blk.res_conv.folded()
-            w2[n] = wr.to(dev)[:, :, 0] * math.sqrt(0.5)         # WaveNet.py:97
+            w2[n] = wr.to(dev)[:, :, 0] * math.sqrt(0.5) * 0.5   # WaveNet.py:97; x 1/2: the kernels keep 2 x gate
             b_res[n] = br.to(dev)
             wsk, bsk = blk.skip_conv.folded()
-            ws[:, n * 256:(n + 1) * 256] = wsk.to(dev)[:, :, 0] * rs
+            ws[:, n * 256:(n + 1) * 256] = wsk.to(dev)[:, :, 0] * (rs * 0.5)   # x 1/2: see above
             bs += bsk.to(dev) * rs
 
         # step embedding for every t (util.py:68-93, WaveNet.py:124-126) and every layer's fc_t (WaveNet.py:82)

@@ -60,12 +60,12 @@ typedef struct ap_config {
 typedef struct ap_weights {
   const void* w1;     /* bf16 (fp32 with AP_FLAG_TF32, also w2/ws/wf) [layers][512][768]: dilated conv, rows gate-interleaved (sigmoid rows x 1/2), K = tap*256 + cin */
   const float* b1;    /* f32  [layers][512]: its bias, same row order and 1/2 factors                       */
-  const void* w2;     /* bf16 [layers][256][256]: sqrt(.5) * res_conv                                      */
+  const void* w2;     /* bf16 [layers][256][256]: 1/2 sqrt(.5) * res_conv (the kernels keep 2 x gate)        */
   const float* c2;    /* f32  [T][layers][256]: sqrt(.5)*b_res[n] + fc_t[n+1](emb(t))  (0 shift for last)  */
   const float* part0; /* f32  [T][256]: fc_t[0](emb(t))                                                    */
   const float* w0;    /* f32  [256]: init conv weight (1 -> 256)                                           */
   const float* b0;    /* f32  [256]                                                                        */
-  const void* ws;     /* bf16 [256][layers*256]: sqrt(1/layers) * skip_conv of every layer, concatenated K */
+  const void* ws;     /* bf16 [256][layers*256]: 1/2 sqrt(1/layers) * skip_conv of every layer, concatenated K */
   const float* bs;    /* f32  [256]: sqrt(1/layers) * sum_n b_skip[n]                                      */
   const void* wf;     /* bf16 [256][256]: final_conv[0]                                                    */
   const float* bf;    /* f32  [256]                                                                        */

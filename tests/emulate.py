@@ -36,7 +36,7 @@ def emulate_eps_tf32(packed, x, t, layers, cycle, return_inter=False):
         gate = []
         for c in range(2):
             blk = d1[..., c * 256:(c + 1) * 256]
-            gate.append(torch.tanh(blk[..., :128]) * torch.sigmoid(2.0 * blk[..., 128:]))  # sigmoid rows are packed halved
+            gate.append(2.0 * torch.tanh(blk[..., :128]) * torch.sigmoid(2.0 * blk[..., 128:]))  # sigmoid rows are packed halved; the kernels keep 2 x gate (1/2 folded into w2 / ws)
         gate = _tf32(torch.cat(gate, dim=-1))
         gates.append(gate)
         h = h * 0.70710678118654752440 + gate @ packed["w2"][n].float().t() + packed["c2"][t, n].float()
@@ -68,7 +68,7 @@ def emulate_eps(packed, x, t, layers, cycle, quantize=True, return_inter=False):
         gate = []
         for c in range(2):
             blk = d1[..., c * 256:(c + 1) * 256]
-            gate.append(torch.tanh(blk[..., :128]) * torch.sigmoid(2.0 * blk[..., 128:]))  # sigmoid rows are packed halved
+            gate.append(2.0 * torch.tanh(blk[..., :128]) * torch.sigmoid(2.0 * blk[..., 128:]))  # sigmoid rows are packed halved; the kernels keep 2 x gate (1/2 folded into w2 / ws)
         gate = _bf16(torch.cat(gate, dim=-1), quantize)                 # (B, L, 256) gate channels in order
         gates.append(gate)
         d2 = gate @ packed["w2"][n].float().t()

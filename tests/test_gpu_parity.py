@@ -141,7 +141,7 @@ def test_eps_dilation_2048_layer_vs_golden(full_model, golden):
     sd = W.make_state_dict(1234)
     for n in (0, 11, 35):
         gate = ws[2 * h_bytes + n * h_bytes: 2 * h_bytes + (n + 1) * h_bytes].view(torch.bfloat16).view(16000, 256)
-        gate = gate.float().cpu()[idx]                                         # (64, 256)
+        gate = 0.5 * gate.float().cpu()[idx]                                   # (64, 256); the kernels keep 2 x gate
         ws_n = o_wavenet.fold_weight_norm(sd["residual_layer.residual_blocks.%d.skip_conv.weight_g" % n],
                                           sd["residual_layer.residual_blocks.%d.skip_conv.weight_v" % n])[:, :, 0]
         skip = gate @ ws_n.t() + sd["residual_layer.residual_blocks.%d.skip_conv.bias" % n]

@@ -14,8 +14,6 @@
 // K = input channels (x taps).  A = activations, B = weights, both K-major, 128-byte swizzle.
 #pragma once
 
-#include <type_traits>
-
 #include "sm100.cuh"
 
 namespace ap {
@@ -29,6 +27,12 @@ constexpr int kEpiThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr float kSqrtHalf = 0.70710678118654752440f;
 
+
+// A compile-time integer that converts to int in device code (std::integral_constant's conversion is host-only).
+template <int V>
+struct IntC {
+  __device__ constexpr operator int() const { return V; }
+};
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -527,11 +531,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
     }
   } else if (warp >= kEpiWarp0) {
     // ======================= epilogue (8 warps, each owns rows [32q,+32) of 64-channel chunks {hh, 2+hh}) ====
-    // The body is instantiated once per warpgroup (hh = 0 / 1) with the chunk and half loops unrolled, so that every
-    // bias index is a compile-time constant and the adds read the constant bank directly instead of through LDC.
+    // bf16: the body is instantiated once per warpgroup (hh = 0 / 1) with the chunk and half loops unrolled, so that
+    // every bias index is a compile-time constant and the adds read the constant bank through warp-uniform loads
+    // instead of per-thread LDC (-2.9 % per launch, profiles/r02_ablation.md).  tf32 keeps ONE rolled copy.
     const int q = warp & 3;   // TMEM lane quarter this warp may read
     auto epilogue = [&](auto hh_c) {
-    constexpr int hh = decltype(hh_c)::value;  // warpgroup: which 64-channel chunks / which half of a gate chunk
+    const int hh = hh_c;  // warpgroup: which 64-channel chunks / which half of a gate chunk (a constant in the bf16 build)
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t gate_ready0 = mapa_u32(&gate_ready[0], 0);
@@ -549,7 +554,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       __syncwarp();
 
       // ---- gate: two chunks of 128 gate channels; this warp does channels [64hh, 64hh+64) of each ----
-#pragma unroll
+      // (bf16: unrolled, so the bias indices are constants; tf32: its accurate tanhf / exp2f gate is ~10x the code,
+      // four unrolled copies of it overflow the instruction cache -- measured 0.86 -> 1.10 ms per launch)
+#pragma unroll(kTf32 ? 1 : 2)
       for (int c = 0; c < 2; ++c) {
         mbar_wait(&d1_full[c], p, 7);
         tc_fence_after();
@@ -607,7 +614,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
         mbar_arrive(tile_free);
       }
       __syncwarp();
-#pragma unroll
+#pragma unroll(kTf32 ? 1 : 2)
       for (int kk = 0; kk < 2; ++kk) {
         const int k = hh + 2 * kk;  // 64-channel chunk
         uint32_t r0[32], r1[32];
@@ -670,10 +677,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ C
       }
     }
     };
-    if (((warp - kEpiWarp0) >> 2) == 0)
-      epilogue(std::integral_constant<int, 0>{});
+    if constexpr (kTf32)
+      epilogue((warp - kEpiWarp0) >> 2);  // one copy: the accurate gate is large, see above
+    else if (((warp - kEpiWarp0) >> 2) == 0)
+      epilogue(IntC<0>{});
     else
-      epilogue(std::integral_constant<int, 1>{});
+      epilogue(IntC<1>{});
     if (lane == 0) tma_store_wait_all();
   }
 

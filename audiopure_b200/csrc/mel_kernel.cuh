@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kFwdThreads, 7) logmel_kernel(const MelArgs a)
   __shared__ __align__(16) float2 zs[16 * kRowPad];  // exchange buffer, then Z[k] in natural order, then the two power spectra
   __shared__ __align__(16) float fbw[kMaxFbNnz];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   // filterbank weights -> shared memory, asynchronously (consumed after the first transform)
   for (int i = tid * 4; i < a.fb_nnz; i += kFwdThreads * 4) {
     if (i + 4 <= a.fb_nnz && (reinterpret_cast<uintptr_t>(a.fb_w) & 15) == 0) {

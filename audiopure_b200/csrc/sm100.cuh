@@ -336,7 +336,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
 //    s_half = s / 2 and sigmoid(s) = 1/2 tanh(s_half) + 1/2 needs no multiply on the way in;
 //  * the kernels produce and store TWICE the gate, 2 tanh(t) sigmoid(s) = tanh(t) (tanh(s_half) + 1) -- one FMA after
 //    the two MUFU ops -- and the factor 1/2 lives in the packed res / skip weights that consume it.
-// Scaling by 2 commutes with rounding to bf16 / tf32, so the results are bit-identical to the unfolded form.
+// The power-of-two scalings are exact (they commute with rounding to bf16 / tf32); the single FMA replaces an FMA
+// followed by a multiply, i.e. it drops one fp32 rounding before the value is rounded to bf16 / tf32.
 #ifdef AP_AB_NO_FOLD  // timing-only A/B variant (profiles/r02_ablation.md): the round-1 epilogue's extra multiplies
 __device__ __forceinline__ float gate2_fast(float t, float s_half) {
   return 2.0f * (tanh_fast(t) * fmaf(0.5f, tanh_fast(0.5f * s_half), 0.5f));

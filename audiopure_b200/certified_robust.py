@@ -13,10 +13,10 @@ num_classes)``, ``certify``, ``smooth_predict``, ``compute_t_star``, ``lower_con
   12-draw slivers of a 64-batch for the n_0 = 100 pass;
 * votes are counted on the device into int64 counters per (pass, clip) (certified_robust.py:58-67) and read back
   once per call; the Clopper-Pearson bound and the radius stay on the host in float64 like the reference;
-* with ``world_size > 1`` each rank takes a contiguous slice of the work list and only the vote counts are
-  all-reduced, once per call (NCCL via the C ABI, or any ``allreduce`` callable -- gloo in the CPU tests).  Because
-  the noise is keyed on (clip, draw), the draws -- and therefore the summed integer counts -- do not depend on the
-  number of ranks or on the batch size.
+* with ``world_size > 1`` the list's BATCHES are dealt out contiguously over the ranks and only the vote counts are
+  all-reduced, once per call (NCCL via the C ABI, or any ``allreduce`` callable -- gloo in the CPU tests).  The
+  noise is keyed on (clip, draw) and a draw sits in the same batch at the same row at every world size, so the
+  summed integer counts do not depend on the number of ranks (all ranks must use the same ``batch_size``).
 """
 
 import ctypes
@@ -36,12 +36,18 @@ def shard_range(n, rank, world_size):
 
 
 def work_batches(n_clips, per_clip, rank, world_size, batch_size):
-    """The launch plan of one certify call on one rank: the clip-major work list of ``n_clips * per_clip``
-    (clip, draw) items is split contiguously over the ranks (``shard_range``), and this rank's slice is cut into
-    full batches -- which may span clips -- plus at most one ragged batch.  Yields (first flat item, rows)."""
-    lo, hi = shard_range(n_clips * per_clip, rank, world_size)
-    for s in range(lo, hi, batch_size):
-        yield s, min(batch_size, hi - s)
+    """The launch plan of one certify call on one rank.  The clip-major work list of ``n_clips * per_clip``
+    (clip, draw) items is cut into batches of ``batch_size`` items FIRST -- full batches that may span clips, plus
+    one ragged batch at the very end -- and the BATCHES are then dealt out contiguously over the ranks
+    (``shard_range``).  A given item therefore sits in the same batch, at the same row, next to the same neighbours
+    whatever the number of ranks, so even a consumer whose kernels are only reproducible per batch position (cuDNN /
+    cuBLASLt stream-K style reductions) votes identically at every world size.  Every rank must use the same
+    ``batch_size``.  Yields (first flat item, rows)."""
+    total = n_clips * per_clip
+    n_batches = (total + batch_size - 1) // batch_size
+    lo, hi = shard_range(n_batches, rank, world_size)
+    for j in range(lo, hi):
+        yield j * batch_size, min(batch_size, total - j * batch_size)
 
 
 def flat_to_clip_draw(flat, per_clip, first_draw=0):
@@ -149,9 +155,9 @@ class RobustCertificate():
 
     def _count_votes(self, x, per_clip, n_split, first_draw, sigma, batch_size, z, clip_key0):
         """Votes of every (clip, draw) pair, draw in [0, per_clip), of the clips ``x`` (C, L): the clip-major work
-        list is cut into this rank's contiguous slice and then into FULL batches that may span clips, so neither a
-        small n_0 nor many ranks leaves the GPU with a sliver of a batch.  Returns int64 device counts [2][C][K]
-        (draws < n_split | draws >= n_split), summed over ranks with ONE all-reduce."""
+        list is cut into FULL batches that may span clips and the batches are dealt out over the ranks
+        (``work_batches``), so neither a small n_0 nor many ranks leaves the GPU with a sliver of a batch.  Returns
+        int64 device counts [2][C][K] (draws < n_split | draws >= n_split), summed over ranks with ONE all-reduce."""
         lib = _lib.load()
         if not x.is_cuda:
             raise _lib.AudioPureError("smooth_predict / certify run on a CUDA device only (no CPU fallback)")

@@ -24,25 +24,31 @@ def test_shard_range_partitions_every_draw_once():
 
 def test_work_batches_cover_every_clip_draw_pair_once_with_full_batches():
     """The certify work list (clips x (n_0 + n) draws, clip-major) over 1..8 ranks: every (clip, draw) pair lands in
-    exactly one batch of one rank, every batch but a rank's last is full, and the n_0 / n split is by draw index."""
+    exactly one batch of one rank, every batch but the globally last one is full, the batches are THE SAME at every
+    world size (an item keeps its batch and its row), and the n_0 / n split is by draw index."""
     for clips, n_0, n, bs in ((1, 100, 10000, 64), (4, 100, 10000, 64), (3, 5, 21, 8), (2, 32, 128, 64), (5, 1, 1, 7)):
         per_clip = n_0 + n
+        single = list(work_batches(clips, per_clip, 0, 1, bs))
+        assert all(b == bs for _, b in single[:-1]) and 0 < single[-1][1] <= bs
         for world in (1, 2, 3, 8):
             seen = set()
+            merged = []
             for r in range(world):
                 batches = list(work_batches(clips, per_clip, r, world, bs))
-                assert all(b == bs for _, b in batches[:-1]) and all(0 < b <= bs for _, b in batches)
+                merged += batches
                 for s, b in batches:
                     for flat in range(s, s + b):
                         item = flat_to_clip_draw(flat, per_clip)
                         assert item not in seen
                         seen.add(item)
+            assert merged == single                       # same batches, same order, whatever the world size
+            counts = [len(list(work_batches(clips, per_clip, r, world, bs))) for r in range(world)]
+            assert max(counts) - min(counts) <= 1         # ranks differ by at most one batch
             assert seen == {(c, d) for c in range(clips) for d in range(per_clip)}
-            sel = sum(1 for c, d in seen if d < n_0)
-            assert sel == clips * n_0
-    # 8 GPUs, BASELINE configs[3]: 1263 or 1262 draws per rank = 19 full batches + one of 47 / 46, instead of the
-    # 12-13-draw slivers a per-clip, per-pass split of n_0 = 100 gives
-    assert [b for _, b in work_batches(1, 10100, 0, 8, 64)][-1] == 1263 - 19 * 64
+            assert sum(1 for c, d in seen if d < n_0) == clips * n_0
+    # 8 GPUs, bench.py's certify leg (4 clips x 10100 draws = 632 batches of 64): 79 batches per rank, all full but the
+    # last one of the last rank -- instead of the 12-13-draw slivers a per-clip, per-pass split of n_0 = 100 gives
+    assert [len(list(work_batches(4, 10100, r, 8, 64))) for r in range(8)] == [79] * 8
 
 
 def _worker(rank, world, port, n, ret):

@@ -243,10 +243,13 @@ def certify_leg(args, ap, S, model, hp, clf, dev, rank, world):
             self.spans.append((e0, e1))
             return out
 
-    # cuDNN autotuning picks its convolution algorithms by timing, so two processes can choose differently and the bf16
-    # consumer's logits then differ in the last bits -- enough to flip a near-tie draw's vote.  With autotuning off
-    # (and RobustCertificate's fixed batch shape) every rank of every N runs the same kernels and the vote counts
-    # are identical at every N: `counts_checksum`.
+    # `counts_checksum` is informational.  The package's own kernels and the Philox noise are invariant to the number of
+    # ranks, and a draw keeps its batch row at every N (work_batches), so with a deterministic consumer the counts
+    # are bit-equal at every N (tools/multigpu_check.py, fp32 module).  The bf16 cuDNN consumer used here runs the
+    # algorithms this PROCESS autotuned in the main leg (PyTorch consults its autotune cache even with autotuning
+    # switched off), and two processes can pick differently, which can flip near-tie votes: measured checksums agree
+    # between most runs and differ by a few votes in some.  Running this leg before anything autotunes makes them
+    # identical everywhere but costs 11 % (cuDNN's heuristic choice for the grouped bf16 convolutions is 3x slower).
     torch.backends.cudnn.benchmark = False
     allreduce = TimedAllReduce(rank, world)  # a 1-rank communicator at N = 1: the same call path at every N
     n0, n, clips, sigma, bs = args.certify_n0, args.certify_n, args.certify_clips, 0.25, 64

@@ -41,7 +41,8 @@ def work_batches(n_clips, per_clip, rank, world_size, batch_size):
     one ragged batch at the very end -- and the BATCHES are then dealt out contiguously over the ranks
     (``shard_range``).  A given item therefore sits in the same batch, at the same row, next to the same neighbours
     whatever the number of ranks, so even a consumer whose kernels are only reproducible per batch position (cuDNN /
-    cuBLASLt stream-K style reductions) votes identically at every world size.  Every rank must use the same
+    cuBLASLt stream-K style reductions) votes identically at every world size -- provided every process runs the same
+    kernels (cuDNN autotuning may pick differently per process).  Every rank must use the same
     ``batch_size``.  Yields (first flat item, rows)."""
     total = n_clips * per_clip
     n_batches = (total + batch_size - 1) // batch_size
